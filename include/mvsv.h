@@ -1,0 +1,135 @@
+/*
+ * mvsv.h -- C ABI of the B200-native stereo disparity engine (libmvsv.so).
+ *
+ * This is the drop-in boundary for mvStereoVision3's hot path.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repository root).  Plain
+ * pointers and sizes only; no C++/torch/OpenCV types cross this line.  All functions return
+ * MVSV_OK (0) or a negative error code and never throw; mvsv_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device mvsv_init fails with MVSV_ERR_CUDA.
+ *
+ * Threading contract (reference: one worker std::thread calls Disparity::sgbm,
+ * trgt/demo.cpp:68-77,195): a ctx is thread-compatible -- any thread may call, one at a time.
+ * Several ctxs (one per GPU or stream) may run concurrently.
+ */
+#ifndef MVSV_H_
+#define MVSV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvsv_ctx mvsv_ctx;
+
+enum {
+    MVSV_OK = 0,
+    MVSV_ERR_INVALID = -1,     /* bad argument / parameter outside the bit-exact contract */
+    MVSV_ERR_CUDA = -2,        /* CUDA runtime error (text in mvsv_last_error)            */
+    MVSV_ERR_NOMEM = -3,
+    MVSV_ERR_STATE = -4,       /* call order (e.g. compute before set_*_params)           */
+    MVSV_ERR_UNSUPPORTED = -5
+};
+
+/* stage bit-mask for mvsv_compute* */
+enum {
+    MVSV_STAGE_RECTIFY = 1,    /* cv::remap x2 + crop      src/Stereosystem.cpp:252-256 */
+    MVSV_STAGE_SGBM = 2,       /* Disparity::sgbm          src/disparity.cpp:6-10       */
+    MVSV_STAGE_BM = 4,         /* Disparity::bm            src/disparity.cpp:18-22      */
+    MVSV_STAGE_XYZ = 8,        /* Utility::dmap2pcl loop   src/utility.cpp:242-262      */
+    MVSV_STAGE_MEANS = 16      /* Utility::calcMeanDisparity per ROI  src/utility.cpp:265-285 */
+};
+
+/* Field order of the first nine ints == struct Disparity::sgbmParameters (inc/disparity.h:17-27).
+ * P1/P2 are never set by the reference (src/disparity.cpp:83-90): leave 0 to get OpenCV's 2 / 5. */
+typedef struct mvsv_sgbm_params {
+    int minDisp, numDisp, blockSize, disp12MaxDiff, preFilterCap, uniquenessRatio;
+    int speckleWindowSize, speckleRange, disparityMode; /* 1 = MODE_HH (8 paths), else MODE_SGBM (5 paths) */
+    int P1, P2;
+} mvsv_sgbm_params;
+
+/* cv::StereoBM state as driven by configs/bm.yml (PREFILTER_XSOBEL, minDisparity 0). */
+typedef struct mvsv_bm_params {
+    int numDisp, blockSize, preFilterCap, textureThreshold, uniquenessRatio;
+} mvsv_bm_params;
+
+typedef struct mvsv_info {
+    int frame_width, frame_height;   /* raw camera frame                                        */
+    int width, height;               /* rectified + cropped pair == disparity map size          */
+    int max_batch;
+    int sgbm_minX1, sgbm_W1, sgbm_D, sgbm_Dpad, sgbm_npaths;   /* evaluated cost domain          */
+    int num_rois;
+    int device;
+} mvsv_info;
+
+/* Create an engine on CUDA device `device` for raw frames of frame_width x frame_height, holding up to
+ * max_batch stereo pairs in flight per compute call.  Replaces the cv::Ptr<cv::StereoSGBM>/StereoBM
+ * objects the drivers create (trgt/demo.cpp:190-194) and Stereosystem's rectification state. */
+int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv_ctx** out);
+void mvsv_destroy(mvsv_ctx* ctx);
+const char* mvsv_last_error(const mvsv_ctx* ctx); /* ctx may be NULL: error of the last failed mvsv_init */
+
+/* Replaces the eight StereoSGBM setters + setMode of Disparity::loadSGBMParameters
+ * (src/disparity.cpp:83-95).  Parameters outside the bit-exact contract are rejected:
+ * numDisp in [8,256] and a multiple of 8; blockSize^2*(2*ftzero+63)+P2 <= 32767. */
+int mvsv_set_sgbm_params(mvsv_ctx* ctx, const mvsv_sgbm_params* p);
+/* cv::StereoBM::create(numDisp, blockSize) + setters (trgt/disparityTest.cpp:268, configs/bm.yml). */
+int mvsv_set_bm_params(mvsv_ctx* ctx, const mvsv_bm_params* p);
+
+/* Replaces Stereosystem::initRectification's map state (src/Stereosystem.cpp:214-220): float CV_32FC1
+ * maps of one camera (cam 0 = left, 1 = right), frame-sized, plus mDisplayROI.  The maps are converted once
+ * to OpenCV's fixed-point (CV_16SC2 + 5-bit fractions) form on the device.  stride is in bytes. */
+int mvsv_upload_rectify_maps(mvsv_ctx* ctx, int cam, const float* mapx, const float* mapy, size_t stride_bytes,
+                             int roi_x, int roi_y, int roi_w, int roi_h);
+/* Stereosystem::resetRectification (src/Stereosystem.cpp:317-320): inputs are taken as already rectified. */
+int mvsv_reset_rectification(mvsv_ctx* ctx);
+
+/* Q as the CV_32F copy the drivers hold (trgt/demo.cpp:179-180), row-major 4x4. */
+int mvsv_set_Q(mvsv_ctx* ctx, const float q[16]);
+/* ROIs (x, y, w, h quadruples in disparity-map coordinates) whose mean disparity is wanted:
+ * the 81 Subimages (src/MeanDisparityDetection.cpp:80-93) and/or the 5x5 Samplepoint windows
+ * (src/SamplePointDetection.cpp:38-47), already shifted by the dMapROI offset (trgt/demo.cpp:87-113). */
+int mvsv_set_mean_rois(mvsv_ctx* ctx, const int* xywh, int n);
+
+/* One pass of the hot path over `batch` stereo pairs held in HOST memory (pair i at base + i*frame_stride).
+ * Asynchronous on the ctx stream when the host buffers are pinned (mvsv_host_alloc); pageable buffers are
+ * staged through ctx-owned pinned memory.  With MVSV_STAGE_RECTIFY the inputs are raw frames (frame size),
+ * otherwise rectified pairs (width x height of mvsv_get_info).  Strides in bytes. */
+int mvsv_compute(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
+                 size_t frame_stride, int batch, unsigned stages);
+/* Same, inputs already resident in device memory (used for the HBM-resident bench figure and pipelines
+ * that produce frames on the GPU). */
+int mvsv_compute_device(mvsv_ctx* ctx, const uint8_t* dleft, size_t lstride, const uint8_t* dright, size_t rstride,
+                        size_t frame_stride, int batch, unsigned stages);
+/* Copy results of the last compute back to host memory and synchronise.  Any pointer may be NULL.
+ *   disp  : batch x height x (dstride bytes per row) int16, CV_16S x16 fixed point, INVALID=(minD-1)*16
+ *   rectL/R: batch x height x (rstride bytes) uint8
+ *   xyz   : batch x height x width x 3 float (0,0,0 where disparity <= 0)
+ *   means : batch x num_rois float */
+int mvsv_download(mvsv_ctx* ctx, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride,
+                  float* xyz, float* means);
+int mvsv_sync(mvsv_ctx* ctx);
+
+int mvsv_get_info(const mvsv_ctx* ctx, mvsv_info* info);
+/* The CUDA stream (cudaStream_t) all work of this ctx is issued on -- for CUDA-event timing by the caller. */
+void* mvsv_stream(mvsv_ctx* ctx);
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+unsigned long long mvsv_launch_count(const mvsv_ctx* ctx);
+
+/* Pinned host memory for zero-staging async copies. */
+int mvsv_host_alloc(void** p, size_t bytes);
+int mvsv_host_free(void* p);
+
+/* Test hooks: read an internal device buffer of the last compute into host memory.
+ * which: 0 = cost volume C, 1 = aggregated S (before the final right-to-left pass), 2 = raw disparity
+ * (after LR check, before median), 3 = vertical-sum volume, 4 = disparity after median (before speckle),
+ * 5 = BM prefiltered left, 6 = BM prefiltered right.  Returns bytes written or a negative error. */
+/* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1). */
+int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
+long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSV_H_ */

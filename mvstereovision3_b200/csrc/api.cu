@@ -1,0 +1,513 @@
+// C-ABI glue of libmvsv.so (include/mvsv.h): context, device buffers, parameter normalisation, stage sequencing.
+#include "mvsv_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace {
+
+thread_local std::string g_init_error;
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define MVSV_CK(ctx, call)                                                                      \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return e_ == cudaErrorMemoryAllocation ? MVSV_ERR_NOMEM : MVSV_ERR_CUDA;            \
+        }                                                                                       \
+    } while (0)
+
+template <class T>
+void dfree(T*& p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int fail(mvsv_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+
+void free_images(mvsv_ctx* c)
+{
+    for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->planes[i]); dfree(c->bm_pre[i]); }
+    dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
+    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means);
+}
+void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); c->vol_elems = 0; }
+void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
+
+int alloc_images(mvsv_ctx* c)
+{
+    free_images(c);
+    c->pitch = round_up((size_t)c->W, 64);
+    const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
+    for (int i = 0; i < 2; ++i) {
+        MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
+        MVSV_CK(c, cudaMalloc(&c->planes[i], 6 * nimg));
+        MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg));
+    }
+    MVSV_CK(c, cudaMalloc(&c->d2, npx * sizeof(int)));
+    MVSV_CK(c, cudaMalloc(&c->disp_raw, npx * sizeof(int16_t)));
+    MVSV_CK(c, cudaMalloc(&c->disp_med, npx * sizeof(int16_t)));
+    MVSV_CK(c, cudaMalloc(&c->disp, npx * sizeof(int16_t)));
+    MVSV_CK(c, cudaMalloc(&c->labels, npx * sizeof(int)));
+    MVSV_CK(c, cudaMalloc(&c->sizes, npx * sizeof(int)));
+    MVSV_CK(c, cudaMalloc(&c->bm_tex, npx * sizeof(uint16_t)));
+    MVSV_CK(c, cudaMalloc(&c->bm_tex2, npx * sizeof(int)));
+    MVSV_CK(c, cudaMemsetAsync(c->disp, 0, npx * sizeof(int16_t), c->stream));
+    return MVSV_OK;
+}
+
+int normalise_sgbm(mvsv_ctx* c, const mvsv_sgbm_params* p, SgbmNorm* n)
+{
+    n->minD = p->minDisp;
+    n->D = p->numDisp;
+    if (n->D <= 0 || n->D % 8 != 0 || n->D > 256)
+        return fail(c, MVSV_ERR_INVALID, "numDisp must be a positive multiple of 8 and <= 256");
+    int g = 1;
+    while (g * 8 < n->D) g <<= 1;
+    n->G = g; n->Dp = g * 8;
+    n->bs = p->blockSize > 0 ? p->blockSize : 5;
+    n->SW2 = n->SH2 = n->bs / 2;
+    n->ftzero = std::max(p->preFilterCap, 15) | 1;
+    n->uniq = p->uniquenessRatio >= 0 ? p->uniquenessRatio : 10;
+    n->d12 = p->disp12MaxDiff > 0 ? p->disp12MaxDiff : 1;
+    n->P1 = p->P1 > 0 ? p->P1 : 2;
+    n->P2 = std::max(p->P2 > 0 ? p->P2 : 5, n->P1 + 1);
+    n->maxD = n->minD + n->D;
+    n->minX1 = std::max(n->maxD, 0);
+    n->maxX1 = c->W + std::min(n->minD, 0);
+    n->W1 = n->maxX1 - n->minX1;
+    n->INV = (n->minD - 1) * 16;
+    n->mode = p->disparityMode == 1 ? 1 : 0;   // reference src/disparity.cpp:92-95
+    n->npaths = n->mode ? 8 : 5;
+    n->speckleWin = p->speckleWindowSize;
+    n->speckleRange = p->speckleRange;
+    if (n->ftzero > 127) return fail(c, MVSV_ERR_INVALID, "preFilterCap > 127 is outside the supported range");
+    if (n->uniq > 100) return fail(c, MVSV_ERR_INVALID, "uniquenessRatio > 100");
+    const long long eff = 2 * n->SH2 + 1;
+    if (eff * eff * (2 * n->ftzero + 63) + n->P2 > 32767)
+        return fail(c, MVSV_ERR_INVALID,
+                    "blockSize^2*(2*ftzero+63)+P2 > 32767: int16 overflow regime of OpenCV is outside the bit-exact contract");
+    if (n->INV < -32768 || (n->maxD) * 16 > 32767) return fail(c, MVSV_ERR_INVALID, "disparity range does not fit CV_16S");
+    return MVSV_OK;
+}
+
+int ensure_sgbm_volumes(mvsv_ctx* c)
+{
+    const SgbmNorm& n = c->sg;
+    if (n.W1 <= 0) return MVSV_OK;
+    const size_t need = (size_t)c->maxB * c->H * n.W1 * n.Dp;
+    if (need <= c->vol_elems && c->VS) return MVSV_OK;
+    free_sgbm_volumes(c);
+    MVSV_CK(c, cudaMalloc(&c->VS, need * 2));
+    MVSV_CK(c, cudaMalloc(&c->C, need * 2));
+    MVSV_CK(c, cudaMalloc(&c->S, need * 2));
+    c->vol_elems = need;
+    return MVSV_OK;
+}
+
+int normalise_bm(mvsv_ctx* c, const mvsv_bm_params* p, BmNorm* n)
+{
+    n->D = p->numDisp; n->bs = p->blockSize; n->cap = p->preFilterCap; n->tex = p->textureThreshold; n->uniq = p->uniquenessRatio;
+    if (n->D <= 0 || n->D % 16 != 0 || n->D > 256) return fail(c, MVSV_ERR_INVALID, "BM numDisp must be a positive multiple of 16 and <= 256");
+    if (n->bs < 5 || n->bs > 255 || n->bs % 2 == 0) return fail(c, MVSV_ERR_INVALID, "BM blockSize must be odd, 5..255");
+    if (n->cap < 1 || n->cap > 63) return fail(c, MVSV_ERR_INVALID, "BM preFilterCap must be 1..63");
+    if (n->tex < 0 || n->uniq < 0) return fail(c, MVSV_ERR_INVALID, "BM textureThreshold/uniquenessRatio must be >= 0");
+    if ((long long)n->bs * n->bs * 2 * n->cap > 65535) return fail(c, MVSV_ERR_INVALID, "BM blockSize^2*2*cap > 65535 unsupported");
+    int g = 2;
+    while (g * 8 < n->D) g <<= 1;
+    n->G = g; n->Dp = g * 8; n->w2 = n->bs / 2;
+    n->lofs = n->D - 1; n->width1 = c->W - n->D + 1; n->FILT = -16;
+    return MVSV_OK;
+}
+
+int ensure_bm_volumes(mvsv_ctx* c)
+{
+    const BmNorm& n = c->bm;
+    if (n.width1 < 1) return MVSV_OK;
+    const size_t need = (size_t)c->maxB * c->H * n.width1 * n.Dp;
+    if (need <= c->bm_vol_elems && c->bm_col) return MVSV_OK;
+    free_bm_volumes(c);
+    MVSV_CK(c, cudaMalloc(&c->bm_col, need * 2));
+    c->bm_vol_elems = need;
+    return MVSV_OK;
+}
+
+int bind(mvsv_ctx* c)
+{
+    MVSV_CK(c, cudaSetDevice(c->device));
+    return MVSV_OK;
+}
+
+// host -> device copy of `batch` images (w bytes wide, h rows) into dst[b][h][dpitch]
+int upload_images(mvsv_ctx* c, uint8_t* dst, size_t dpitch, const uint8_t* src, size_t sstride, size_t frame_stride, int w,
+                  int h, int batch, bool device_src)
+{
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (frame_stride == sstride * (size_t)h) {
+        MVSV_CK(c, cudaMemcpy2DAsync(dst, dpitch, src, sstride, (size_t)w, (size_t)h * batch, kind, c->stream));
+    } else {
+        for (int b = 0; b < batch; ++b)
+            MVSV_CK(c, cudaMemcpy2DAsync(dst + (size_t)b * h * dpitch, dpitch, src + (size_t)b * frame_stride, sstride, (size_t)w,
+                                         (size_t)h, kind, c->stream));
+    }
+    return MVSV_OK;
+}
+
+int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride, size_t frame_stride, int batch,
+        unsigned stages, bool device_src)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!left || !right || batch < 1 || batch > c->maxB) return fail(c, MVSV_ERR_INVALID, "bad image pointers or batch size");
+    if ((stages & MVSV_STAGE_SGBM) && (stages & MVSV_STAGE_BM)) return fail(c, MVSV_ERR_INVALID, "choose SGBM or BM, not both");
+    if ((stages & MVSV_STAGE_SGBM) && !c->has_sgbm) return fail(c, MVSV_ERR_STATE, "mvsv_set_sgbm_params not called");
+    if ((stages & MVSV_STAGE_BM) && !c->has_bm) return fail(c, MVSV_ERR_STATE, "mvsv_set_bm_params not called");
+    if ((stages & MVSV_STAGE_XYZ) && !c->has_Q) return fail(c, MVSV_ERR_STATE, "mvsv_set_Q not called");
+    if (stages & MVSV_STAGE_RECTIFY) {
+        if (!c->has_maps[0] || !c->has_maps[1]) return fail(c, MVSV_ERR_STATE, "rectify maps missing (mvsv_upload_rectify_maps)");
+        if (lstride < (size_t)c->fw || rstride < (size_t)c->fw) return fail(c, MVSV_ERR_INVALID, "stride smaller than frame width");
+        rc = upload_images(c, c->raw[0], c->raw_pitch, left, lstride, frame_stride, c->fw, c->fh, batch, device_src);
+        if (rc) return rc;
+        rc = upload_images(c, c->raw[1], c->raw_pitch, right, rstride, frame_stride, c->fw, c->fh, batch, device_src);
+        if (rc) return rc;
+        c->launches += launch_remap(c, 0, batch);
+        c->launches += launch_remap(c, 1, batch);
+    } else {
+        if (lstride < (size_t)c->W || rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "stride smaller than image width");
+        rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, c->W, c->H, batch, device_src);
+        if (rc) return rc;
+        rc = upload_images(c, c->rect[1], c->pitch, right, rstride, frame_stride, c->W, c->H, batch, device_src);
+        if (rc) return rc;
+    }
+    if (stages & MVSV_STAGE_SGBM) {
+        rc = ensure_sgbm_volumes(c);
+        if (rc) return rc;
+        c->launches += launch_sgbm(c, batch);
+    } else if (stages & MVSV_STAGE_BM) {
+        rc = ensure_bm_volumes(c);
+        if (rc) return rc;
+        c->launches += launch_bm(c, batch);
+    }
+    if (stages & MVSV_STAGE_XYZ) {
+        if (!c->xyz) MVSV_CK(c, cudaMalloc(&c->xyz, (size_t)c->maxB * c->H * c->W * 3 * sizeof(float)));
+        c->launches += launch_xyz(c, batch);
+    }
+    if (stages & MVSV_STAGE_MEANS) c->launches += launch_means(c, batch);
+    MVSV_CK(c, cudaGetLastError());
+    c->lastB = batch;
+    c->last_stages = stages;
+    return MVSV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv_ctx** out)
+{
+    if (!out) return MVSV_ERR_INVALID;
+    *out = nullptr;
+    if (frame_width < 2 || frame_height < 1 || frame_width > 16384 || frame_height > 16384 || max_batch < 1 || max_batch > 32767) {
+        g_init_error = "mvsv_init: invalid frame size or batch";
+        return MVSV_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_init_error = std::string("mvsv_init: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback";
+        return MVSV_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_init_error = "mvsv_init: device index out of range";
+        return MVSV_ERR_INVALID;
+    }
+    mvsv_ctx* c = new (std::nothrow) mvsv_ctx();
+    if (!c) return MVSV_ERR_NOMEM;
+    c->device = device; c->fw = frame_width; c->fh = frame_height; c->W = frame_width; c->H = frame_height; c->maxB = max_batch;
+    auto bail = [&](cudaError_t ee, const char* what) {
+        g_init_error = std::string("mvsv_init: ") + what + ": " + cudaGetErrorString(ee);
+        mvsv_destroy(c);
+        return ee == cudaErrorMemoryAllocation ? MVSV_ERR_NOMEM : MVSV_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        g_init_error = "mvsv_init: kernels are built for sm_100a only";
+        mvsv_destroy(c);
+        return MVSV_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = sgbm_configure_kernels()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
+    int rc = alloc_images(c);
+    if (rc) { g_init_error = c->err; mvsv_destroy(c); return rc; }
+    *out = c;
+    return MVSV_OK;
+}
+
+void mvsv_destroy(mvsv_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_images(c);
+    free_sgbm_volumes(c);
+    free_bm_volumes(c);
+    for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); }
+    dfree(c->rois);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* mvsv_last_error(const mvsv_ctx* c) { return c ? c->err.c_str() : g_init_error.c_str(); }
+
+int mvsv_set_sgbm_params(mvsv_ctx* c, const mvsv_sgbm_params* p)
+{
+    if (!c || !p) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    SgbmNorm n;
+    rc = normalise_sgbm(c, p, &n);
+    if (rc) return rc;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->sg = n; c->sgbm_raw = *p; c->has_sgbm = true;
+    return ensure_sgbm_volumes(c);
+}
+
+int mvsv_set_bm_params(mvsv_ctx* c, const mvsv_bm_params* p)
+{
+    if (!c || !p) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    BmNorm n;
+    rc = normalise_bm(c, p, &n);
+    if (rc) return rc;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->bm = n; c->bm_raw = *p; c->has_bm = true;
+    return ensure_bm_volumes(c);
+}
+
+static int resize_rectified(mvsv_ctx* c, int W, int H)
+{
+    if (W == c->W && H == c->H) return MVSV_OK;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->W = W; c->H = H;
+    int rc = alloc_images(c);
+    if (rc) return rc;
+    free_sgbm_volumes(c);
+    free_bm_volumes(c);
+    if (c->has_sgbm) {
+        rc = normalise_sgbm(c, &c->sgbm_raw, &c->sg);
+        if (rc) return rc;
+        rc = ensure_sgbm_volumes(c);
+        if (rc) return rc;
+    }
+    if (c->has_bm) {
+        rc = normalise_bm(c, &c->bm_raw, &c->bm);
+        if (rc) return rc;
+        rc = ensure_bm_volumes(c);
+        if (rc) return rc;
+    }
+    return MVSV_OK;
+}
+
+int mvsv_upload_rectify_maps(mvsv_ctx* c, int cam, const float* mapx, const float* mapy, size_t stride_bytes, int roi_x,
+                             int roi_y, int roi_w, int roi_h)
+{
+    if (!c || !mapx || !mapy || cam < 0 || cam > 1) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (roi_x < 0 || roi_y < 0 || roi_w < 2 || roi_h < 1 || roi_x + roi_w > c->fw || roi_y + roi_h > c->fh)
+        return fail(c, MVSV_ERR_INVALID, "display ROI outside the frame");
+    if (stride_bytes < (size_t)c->fw * sizeof(float) || stride_bytes % sizeof(float)) return fail(c, MVSV_ERR_INVALID, "bad map stride");
+    const int other = 1 - cam;
+    if (c->has_maps[other] && (c->roi[0] != roi_x || c->roi[1] != roi_y || c->roi[2] != roi_w || c->roi[3] != roi_h))
+        return fail(c, MVSV_ERR_INVALID, "both cameras must share one display ROI (mDisplayROI)");
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->roi[0] = roi_x; c->roi[1] = roi_y; c->roi[2] = roi_w; c->roi[3] = roi_h;
+    rc = resize_rectified(c, roi_w, roi_h);
+    if (rc) return rc;
+    if (!c->raw[0]) {
+        c->raw_pitch = round_up((size_t)c->fw, 64);
+        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
+    }
+    dfree(c->map_xy[cam]);
+    MVSV_CK(c, cudaMalloc(&c->map_xy[cam], (size_t)roi_w * roi_h * sizeof(int2)));
+    float *dx = nullptr, *dy = nullptr;
+    const size_t mbytes = (size_t)c->fw * c->fh * sizeof(float);
+    MVSV_CK(c, cudaMalloc(&dx, mbytes));
+    cudaError_t e = cudaMalloc(&dy, mbytes);
+    if (e != cudaSuccess) { cudaFree(dx); c->err = "cudaMalloc(map)"; return MVSV_ERR_NOMEM; }
+    const size_t w = (size_t)c->fw * sizeof(float);
+    e = cudaMemcpy2DAsync(dx, w, mapx, stride_bytes, w, c->fh, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dy, w, mapy, stride_bytes, w, c->fh, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        c->launches += launch_convert_maps(c, cam, dx, dy, (size_t)c->fw);
+        e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(dx); cudaFree(dy);
+    if (e != cudaSuccess) { c->err = std::string("map upload: ") + cudaGetErrorString(e); return MVSV_ERR_CUDA; }
+    c->has_maps[cam] = true;
+    return MVSV_OK;
+}
+
+int mvsv_reset_rectification(mvsv_ctx* c)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    c->has_maps[0] = c->has_maps[1] = false;
+    return resize_rectified(c, c->fw, c->fh);
+}
+
+int mvsv_set_Q(mvsv_ctx* c, const float q[16])
+{
+    if (!c || !q) return MVSV_ERR_INVALID;
+    std::memcpy(c->Q, q, sizeof(float) * 16);
+    c->has_Q = true;
+    return MVSV_OK;
+}
+
+int mvsv_set_mean_rois(mvsv_ctx* c, const int* xywh, int n)
+{
+    if (!c || n < 0 || (n > 0 && !xywh)) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        const int* r = xywh + 4 * i;
+        if (r[0] < 0 || r[1] < 0 || r[2] < 1 || r[3] < 1 || r[0] + r[2] > c->W || r[1] + r[3] > c->H)
+            return fail(c, MVSV_ERR_INVALID, "ROI outside the disparity map");
+    }
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    dfree(c->rois); dfree(c->means);
+    c->nrois = n;
+    if (n == 0) return MVSV_OK;
+    MVSV_CK(c, cudaMalloc(&c->rois, (size_t)n * 4 * sizeof(int)));
+    MVSV_CK(c, cudaMalloc(&c->means, (size_t)n * c->maxB * sizeof(float)));
+    MVSV_CK(c, cudaMemcpy(c->rois, xywh, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice));
+    return MVSV_OK;
+}
+
+int mvsv_compute(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride, size_t frame_stride,
+                 int batch, unsigned stages)
+{
+    return run(c, left, lstride, right, rstride, frame_stride, batch, stages, false);
+}
+
+int mvsv_compute_device(mvsv_ctx* c, const uint8_t* dleft, size_t lstride, const uint8_t* dright, size_t rstride,
+                        size_t frame_stride, int batch, unsigned stages)
+{
+    return run(c, dleft, lstride, dright, rstride, frame_stride, batch, stages, true);
+}
+
+int mvsv_download(mvsv_ctx* c, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride, float* xyz,
+                  float* means)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    const int B = c->lastB;
+    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
+    if (disp) {
+        if (dstride < (size_t)c->W * 2) return fail(c, MVSV_ERR_INVALID, "disparity stride too small");
+        MVSV_CK(c, cudaMemcpy2DAsync(disp, dstride, c->disp, (size_t)c->W * 2, (size_t)c->W * 2, (size_t)c->H * B,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    }
+    uint8_t* r[2] = {rectL, rectR};
+    for (int i = 0; i < 2; ++i)
+        if (r[i]) {
+            if (rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "rectified stride too small");
+            MVSV_CK(c, cudaMemcpy2DAsync(r[i], rstride, c->rect[i], c->pitch, (size_t)c->W, (size_t)c->H * B,
+                                         cudaMemcpyDeviceToHost, c->stream));
+        }
+    if (xyz) {
+        if (!c->xyz || !(c->last_stages & MVSV_STAGE_XYZ)) return fail(c, MVSV_ERR_STATE, "XYZ stage was not computed");
+        MVSV_CK(c, cudaMemcpyAsync(xyz, c->xyz, (size_t)B * c->H * c->W * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (means) {
+        if (!c->means || !(c->last_stages & MVSV_STAGE_MEANS)) return fail(c, MVSV_ERR_STATE, "MEANS stage was not computed");
+        MVSV_CK(c, cudaMemcpyAsync(means, c->means, (size_t)B * c->nrois * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    return MVSV_OK;
+}
+
+int mvsv_sync(mvsv_ctx* c)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    return MVSV_OK;
+}
+
+int mvsv_get_info(const mvsv_ctx* c, mvsv_info* info)
+{
+    if (!c || !info) return MVSV_ERR_INVALID;
+    std::memset(info, 0, sizeof(*info));
+    info->frame_width = c->fw; info->frame_height = c->fh; info->width = c->W; info->height = c->H; info->max_batch = c->maxB;
+    if (c->has_sgbm) {
+        info->sgbm_minX1 = c->sg.minX1; info->sgbm_W1 = c->sg.W1; info->sgbm_D = c->sg.D; info->sgbm_Dpad = c->sg.Dp;
+        info->sgbm_npaths = c->sg.npaths;
+    }
+    info->num_rois = c->nrois; info->device = c->device;
+    return MVSV_OK;
+}
+
+void* mvsv_stream(mvsv_ctx* c) { return c ? (void*)c->stream : nullptr; }
+unsigned long long mvsv_launch_count(const mvsv_ctx* c) { return c ? c->launches : 0ull; }
+
+int mvsv_host_alloc(void** p, size_t bytes)
+{
+    if (!p) return MVSV_ERR_INVALID;
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? MVSV_OK : MVSV_ERR_NOMEM;
+}
+int mvsv_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MVSV_OK : MVSV_ERR_CUDA; }
+
+int mvsv_debug_set_flags(mvsv_ctx* c, unsigned flags)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    c->debug_flags = flags;
+    return MVSV_OK;
+}
+
+long long mvsv_debug_read(mvsv_ctx* c, int which, void* host, size_t cap)
+{
+    if (!c || !host) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    const int B = c->lastB;
+    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const size_t vol = c->has_sgbm && c->sg.W1 > 0 ? (size_t)B * c->H * c->sg.W1 * c->sg.Dp * 2 : 0;
+    const size_t img16 = (size_t)B * c->H * c->W * 2;
+    switch (which) {
+        case 0: src = c->C; bytes = vol; break;
+        case 1: src = c->S; bytes = vol; break;
+        case 2: src = c->disp_raw; bytes = img16; break;
+        case 3: src = c->VS; bytes = vol; break;
+        case 4: src = c->disp_med; bytes = img16; break;
+        case 5: src = c->bm_pre[0]; bytes = (size_t)B * c->H * c->pitch; break;
+        case 6: src = c->bm_pre[1]; bytes = (size_t)B * c->H * c->pitch; break;
+        default: return fail(c, MVSV_ERR_INVALID, "unknown debug buffer");
+    }
+    if (!src || bytes == 0) return fail(c, MVSV_ERR_STATE, "buffer not available");
+    if (bytes > cap) return fail(c, MVSV_ERR_INVALID, "host buffer too small");
+    MVSV_CK(c, cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    return (long long)bytes;
+}
+
+}  // extern "C"

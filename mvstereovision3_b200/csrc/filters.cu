@@ -1,0 +1,285 @@
+// Rectification (K1), 3x3 median (K5), speckle filter (K6), reprojection + ROI means (K8) on sm_100a.
+#include "mvsv_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K1: cv::remap(INTER_LINEAR, CV_32FC1 maps, BORDER_CONSTANT 0) + crop  (reference
+// src/Stereosystem.cpp:252-256; semantics SURVEY.md A.1).  Maps are converted once to fixed point.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_convert_maps(const float* __restrict__ mx, const float* __restrict__ my, size_t strideElems,
+                               int rx, int ry, int rw, int rh, int2* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= rw || y >= rh) return;
+    size_t mi = (size_t)(y + ry) * strideElems + (size_t)(x + rx);
+    out[(size_t)y * rw + x] = make_int2(__float2int_rn(mx[mi] * 32.0f), __float2int_rn(my[mi] * 32.0f));
+}
+
+__device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
+
+__global__ void k_remap(const uint8_t* __restrict__ src, size_t spitch, int fw, int fh, const int2* __restrict__ map,
+                        uint8_t* __restrict__ dst, size_t dpitch, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const int2 m = map[(size_t)y * W + x];
+    const int sx = sat16(m.x >> 5), sy = sat16(m.y >> 5), fx = m.x & 31, fy = m.y & 31;
+    const uint8_t* s = src + (size_t)f * fh * spitch;
+    int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
+    const bool x0 = sx >= 0 && sx < fw, x1 = sx + 1 >= 0 && sx + 1 < fw;
+    if (sy >= 0 && sy < fh) {
+        const uint8_t* r = s + (size_t)sy * spitch;
+        if (x0) p00 = r[sx];
+        if (x1) p01 = r[sx + 1];
+    }
+    if (sy + 1 >= 0 && sy + 1 < fh) {
+        const uint8_t* r = s + (size_t)(sy + 1) * spitch;
+        if (x0) p10 = r[sx];
+        if (x1) p11 = r[sx + 1];
+    }
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 16384) >> 15;
+    dst[((size_t)f * H + y) * dpitch + x] = (uint8_t)max(0, min(255, v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: medianBlur(CV_16S, 3), replicate border (inside StereoSGBM::compute)
+// ------------------------------------------------------------------------------------------------
+#define MVSV_CSWAP(a, b) { const int t_ = min(a, b); b = max(a, b); a = t_; }
+__global__ void k_median3(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int16_t* img = in + (size_t)blockIdx.z * W * H;
+    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+    const int16_t* r0 = img + (size_t)max(y - 1, 0) * W;
+    const int16_t* r1 = img + (size_t)y * W;
+    const int16_t* r2 = img + (size_t)min(y + 1, H - 1) * W;
+    int p0 = r0[xm], p1 = r0[x], p2 = r0[xp], p3 = r1[xm], p4 = r1[x], p5 = r1[xp], p6 = r2[xm], p7 = r2[x], p8 = r2[xp];
+    MVSV_CSWAP(p1, p2) MVSV_CSWAP(p4, p5) MVSV_CSWAP(p7, p8)
+    MVSV_CSWAP(p0, p1) MVSV_CSWAP(p3, p4) MVSV_CSWAP(p6, p7)
+    MVSV_CSWAP(p1, p2) MVSV_CSWAP(p4, p5) MVSV_CSWAP(p7, p8)
+    MVSV_CSWAP(p0, p3) MVSV_CSWAP(p5, p8) MVSV_CSWAP(p4, p7)
+    MVSV_CSWAP(p3, p6) MVSV_CSWAP(p1, p4) MVSV_CSWAP(p2, p5)
+    MVSV_CSWAP(p4, p7) MVSV_CSWAP(p4, p2) MVSV_CSWAP(p6, p4)
+    MVSV_CSWAP(p4, p2)
+    out[(size_t)blockIdx.z * W * H + (size_t)y * W + x] = (int16_t)p4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: filterSpeckles as exact connected components: run-based label-equivalence CCL.
+//   1. rows:    every pixel gets the index of the first pixel of its horizontal run (warp ballot scan)
+//   2. vmerge:  lock-free union (atomicMin) of vertically connected runs, skipping links the left
+//               neighbour already established
+//   3. flatten: label := root; the last pixel of each run adds the run length to the root's size
+//   4. apply:   components with size <= maxSize are set to newVal
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool conn(int a, int b, int newVal, int maxDiff)
+{
+    return a != newVal && b != newVal && abs(a - b) <= maxDiff;
+}
+
+__global__ void k_ccl_rows(const int16_t* __restrict__ img, int* __restrict__ label, int W, int nrows, int newVal,
+                           int maxDiff)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    const size_t base = (size_t)warp * W;
+    int carry = 0;
+    for (int cb = 0; cb < W; cb += 32) {
+        const int x = cb + lane;
+        int v = newVal, vl = newVal;
+        if (x < W) {
+            v = img[base + x];
+            if (x > 0) vl = img[base + x - 1];
+        }
+        const bool valid = (x < W) && v != newVal;
+        const bool start = valid && !conn(v, vl, newVal, maxDiff);
+        const unsigned sb = __ballot_sync(0xffffffffu, start);
+        const unsigned le = sb & (0xffffffffu >> (31 - lane));
+        const int xs = le ? cb + (31 - __clz(le)) : carry;
+        if (x < W) label[base + x] = valid ? (int)(base + xs) : -1;
+        if (sb) carry = cb + (31 - __clz(sb));
+    }
+}
+
+__device__ __forceinline__ int ccl_find(const int* L, int i)
+{
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+
+__device__ __forceinline__ void ccl_unite(int* L, int a, int b)
+{
+    while (true) {
+        a = ccl_find(L, a);
+        b = ccl_find(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int newVal,
+                             int maxDiff)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
+    if (x >= W || y >= H) return;
+    const size_t i = ((size_t)blockIdx.z * H + y) * W + x, u = i - W;
+    const int v = img[i], vu = img[u];
+    if (!conn(v, vu, newVal, maxDiff)) return;
+    if (x > 0) {
+        const int vl = img[i - 1], vul = img[u - 1];
+        if (conn(v, vl, newVal, maxDiff) && conn(vu, vul, newVal, maxDiff) && conn(vl, vul, newVal, maxDiff)) return;
+    }
+    ccl_unite(label, label[i], label[u]);
+}
+
+__global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ sizes, int W,
+                              int H, int newVal, int maxDiff)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t rowBase = ((size_t)blockIdx.z * H + y) * W;
+    const size_t i = rowBase + x;
+    const int l = label[i];
+    if (l < 0) return;
+    const int root = ccl_find(label, l);
+    const int v = img[i];
+    const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
+    const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
+    // labels of run starts are union-find tree links (compressing them towards the root is safe);
+    // labels of the other pixels still hold their run start, which gives the run length.
+    const int xs = runStart ? x : (l - (int)rowBase);
+    label[i] = root;
+    if (runEnd) atomicAdd(&sizes[root], x - xs + 1);
+}
+
+__global__ void k_ccl_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ sizes,
+                            size_t n, int newVal, int maxSize)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = label[i];
+    if (l < 0) return;
+    const int root = ccl_find(label, l);
+    if (sizes[root] <= maxSize) img[i] = (int16_t)newVal;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: reprojection (Utility::calcCoordinate over dmap2pcl's loop, reference src/utility.cpp:176-200,
+// 242-262) and per-ROI mean disparity (Utility::calcMeanDisparity, src/utility.cpp:265-285).
+// ------------------------------------------------------------------------------------------------
+struct QMat { float q[16]; };
+
+__global__ void k_xyz(const int16_t* __restrict__ disp, float* __restrict__ xyz, int W, int H, QMat Q)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
+    const float value = (float)disp[i];
+    float X = 0.f, Y = 0.f, Z = 0.f;
+    if (value > 0.f) {
+        const float in[4] = {(float)x, (float)y, value / 16.f, 1.f};
+        float c[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double acc = 0.0;   // cv::Mat_<float> product accumulates in double
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc += (double)Q.q[r * 4 + k] * (double)in[k];
+            c[r] = (float)acc;
+        }
+        X = c[0] / c[3]; Y = c[1] / c[3]; Z = c[2] / c[3];
+        if (isinf(Z / 1000.f)) Z = 0.f;
+    }
+    xyz[i * 3 + 0] = X; xyz[i * 3 + 1] = Y; xyz[i * 3 + 2] = Z;
+}
+
+__global__ void k_means(const int16_t* __restrict__ disp, const int* __restrict__ rois, float* __restrict__ means,
+                        int W, int H, int nrois)
+{
+    const int r = blockIdx.x, f = blockIdx.y;
+    const int x0 = rois[r * 4 + 0], y0 = rois[r * 4 + 1], w = rois[r * 4 + 2], h = rois[r * 4 + 3];
+    const int16_t* img = disp + (size_t)f * W * H;
+    int total = 0, n = 0;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int v = img[(size_t)(y0 + i / w) * W + x0 + i % w];
+        if (v > 1) { total += v; ++n; }
+    }
+    __shared__ int st[32], sn[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) { st[threadIdx.x >> 5] = total; sn[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        total = 0; n = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { total += st[i]; n += sn[i]; }
+        means[(size_t)f * nrois + r] = (total == 0 || n == 0) ? 0.f : (float)(total / n);
+    }
+}
+
+}  // namespace
+
+int launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t strideElems)
+{
+    dim3 blk(128), grd((c->roi[2] + 127) / 128, c->roi[3]);
+    k_convert_maps<<<grd, blk, 0, c->stream>>>(dmapx, dmapy, strideElems, c->roi[0], c->roi[1], c->roi[2], c->roi[3],
+                                               c->map_xy[cam]);
+    return 1;
+}
+
+int launch_remap(mvsv_ctx* c, int cam, int B)
+{
+    dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    k_remap<<<grd, blk, 0, c->stream>>>(c->raw[cam], c->raw_pitch, c->fw, c->fh, c->map_xy[cam], c->rect[cam], c->pitch,
+                                        c->W, c->H);
+    return 1;
+}
+
+int launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
+{
+    dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    k_median3<<<grd, blk, 0, c->stream>>>(in, out, c->W, c->H);
+    return 1;
+}
+
+int launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff)
+{
+    const int W = c->W, H = c->H;
+    const size_t n = (size_t)B * W * H;
+    cudaMemsetAsync(c->sizes, 0, n * sizeof(int), c->stream);
+    const int nrows = B * H;
+    k_ccl_rows<<<(nrows * 32 + 127) / 128, 128, 0, c->stream>>>(img, c->labels, W, nrows, newVal, maxDiff);
+    dim3 blk(128), grd((W + 127) / 128, H, B);
+    if (H > 1) {
+        dim3 grdv((W + 127) / 128, H - 1, B);
+        k_ccl_vmerge<<<grdv, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
+    }
+    k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff);
+    k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, c->labels, c->sizes, n, newVal, maxSize);
+    return H > 1 ? 4 : 3;
+}
+
+int launch_xyz(mvsv_ctx* c, int B)
+{
+    QMat Q;
+    for (int i = 0; i < 16; ++i) Q.q[i] = c->Q[i];
+    dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    k_xyz<<<grd, blk, 0, c->stream>>>(c->disp, c->xyz, c->W, c->H, Q);
+    return 1;
+}
+
+int launch_means(mvsv_ctx* c, int B)
+{
+    if (c->nrois <= 0) return 0;
+    dim3 grd(c->nrois, B);
+    k_means<<<grd, 128, 0, c->stream>>>(c->disp, c->rois, c->means, c->W, c->H, c->nrois);
+    return 1;
+}

@@ -1,0 +1,101 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI glue (libmvsv.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/mvsv.h"
+
+#define MVSV_MAX_COST 32767
+#define MVSV_PK_MAX 0x7fff7fffu
+
+// Normalised StereoSGBM parameters (OpenCV's own normalisation of the values that
+// Disparity::loadSGBMParameters hands over, reference src/disparity.cpp:83-95).
+struct SgbmNorm {
+    int minD, D, Dp, G;          // Dp = G*8 padded disparity count, G = lanes per pixel (power of two)
+    int bs, SW2, SH2, ftzero, uniq, d12, P1, P2;
+    int maxD, minX1, maxX1, W1, INV, mode, npaths;
+    int speckleWin, speckleRange;
+};
+
+struct BmNorm {
+    int D, Dp, G, bs, w2, cap, tex, uniq;
+    int lofs, width1, FILT;
+};
+
+struct mvsv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int fw = 0, fh = 0;          // raw frame
+    int W = 0, H = 0;            // rectified/cropped pair
+    int maxB = 0;
+    int lastB = 0;
+    unsigned last_stages = 0;
+    unsigned long long launches = 0;
+    unsigned debug_flags = 0;   // bit0: h2 pass stores the final S volume (test hook)
+    std::string err;
+
+    // rectification (device): per camera, fixed-point maps for the ROI only
+    bool has_maps[2] = {false, false};
+    int roi[4] = {0, 0, 0, 0};
+    int2* map_xy[2] = {nullptr, nullptr};     // (ix, iy) = rint(map*32), saturated int32
+    uint8_t* raw[2] = {nullptr, nullptr};     // [B][fh][raw_pitch]
+    size_t raw_pitch = 0;
+
+    uint8_t* rect[2] = {nullptr, nullptr};    // [B][H][pitch]
+    size_t pitch = 0;
+
+    bool has_sgbm = false, has_bm = false;
+    mvsv_sgbm_params sgbm_raw{};
+    SgbmNorm sg{};
+    mvsv_bm_params bm_raw{};
+    BmNorm bm{};
+
+    uint8_t* planes[2] = {nullptr, nullptr};  // 6 prefilter planes per image: [6][B][H][pitch]
+    uint16_t* VS = nullptr;                   // [B][H][W1][Dp] vertical box sums of the pixel cost
+    uint16_t* C = nullptr;                    // [B][H][W1][Dp] block cost
+    uint16_t* S = nullptr;                    // [B][H][W1][Dp] aggregated cost
+    size_t vol_elems = 0;                     // elements allocated per volume
+    int* d2 = nullptr;                        // [B][H][W] (disp2cost<<16 | disp2)
+    int16_t* disp_raw = nullptr;              // [B][H][W]
+    int16_t* disp_med = nullptr;              // [B][H][W]
+    int16_t* disp = nullptr;                  // final [B][H][W]
+    int* labels = nullptr;                    // [B][H][W]
+    int* sizes = nullptr;                     // [B][H][W]
+
+    uint8_t* bm_pre[2] = {nullptr, nullptr};  // [B][H][pitch]
+    uint16_t* bm_tex = nullptr;               // [B][H][W] column sums, then window sums (int32 below)
+    int* bm_tex2 = nullptr;
+    size_t bm_vol_elems = 0;
+    uint16_t* bm_col = nullptr;               // [B][H][width1][Dp]
+
+    bool has_Q = false;
+    float Q[16];
+    float* xyz = nullptr;                     // [B][H][W][3]
+    int nrois = 0;
+    int* rois = nullptr;                      // device [n][4]
+    float* means = nullptr;                   // device [B][n]
+
+    // pinned staging for pageable host buffers
+    uint8_t* stage = nullptr;
+    size_t stage_bytes = 0;
+};
+
+// ---- kernel launchers (each returns the number of kernel launches it issued) ------------------------
+int launch_remap(mvsv_ctx* c, int cam, int B);
+int launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t stride_elems);
+int launch_sgbm(mvsv_ctx* c, int B);
+int launch_bm(mvsv_ctx* c, int B);
+int launch_xyz(mvsv_ctx* c, int B);
+int launch_means(mvsv_ctx* c, int B);
+int launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
+int launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff);
+cudaError_t sgbm_configure_kernels();
+
+#ifdef __CUDACC__
+// ---- packed 16x2 helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pk16(int v) { return ((unsigned)v & 0xffffu) * 0x10001u; }
+__device__ __forceinline__ uint4 ld128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st128(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+#endif

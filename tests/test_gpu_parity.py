@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle, the committed cv2 golden
+vectors and (when cv2 is importable) cv2 4.13.0 live at the BASELINE.json sizes.  Integer outputs are bit-exact;
+float XYZ within 1e-5 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from mvstereovision3_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(cases.GOLDEN_DIR, "cv2_golden.npz"))
+
+
+def gpu_params(p):
+    d = dict(p)
+    d["disparityMode"] = d.pop("mode")
+    return d
+
+
+def first_diff(a, b):
+    idx = np.argwhere(a != b)
+    return "%d mismatches, first at %s: got %s want %s" % (len(idx), tuple(idx[0]), a[tuple(idx[0])], b[tuple(idx[0])])
+
+
+def check(name, got, want):
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    assert np.array_equal(got, want), "%s: %s" % (name, first_diff(got, want))
+
+
+@pytest.mark.parametrize("case", cases.SGBM_CASES, ids=[c[0] for c in cases.SGBM_CASES])
+def test_sgbm_stages_vs_oracle(oracle, golden, case):
+    name, p, H, W = case
+    with api.Engine(W, H, max_batch=2) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.debug_set_flags(1)
+        pair = [cases.sgbm_inputs(name, p, H, W, k) for k in ("ramp", "noise")]
+        left = np.stack([pair[0][0], pair[1][0]])
+        right = np.stack([pair[0][1], pair[1][1]])
+        e.compute(left, right, api.STAGE_SGBM)
+        out = e.download(2)["disp"]
+        Cg, Sg, raw, med = (e.debug_read(w, 2) for w in (0, 1, 2, 4))
+        for b, kind in enumerate(("ramp", "noise")):
+            disp, Cv, Sv, rawv = oracle.sgbm(pair[b][0], pair[b][1], p, want_volumes=True, want_raw=True)
+            check(name + "/C/" + kind, Cg[b], Cv)
+            check(name + "/S/" + kind, Sg[b], Sv)
+            check(name + "/raw/" + kind, raw[b], rawv)
+            check(name + "/median/" + kind, med[b], oracle.median3(rawv))
+            check(name + "/disp/" + kind, out[b], disp)
+            check(name + "/golden/" + kind, out[b], golden["sgbm/%s/%s" % (name, kind)])
+
+
+@pytest.mark.parametrize("case", cases.BM_CASES, ids=[c[0] for c in cases.BM_CASES])
+def test_bm_vs_oracle(oracle, golden, case):
+    name, p, H, W = case
+    with api.Engine(W, H, max_batch=2) as e:
+        e.set_bm_params(**p)
+        pair = [cases.bm_inputs(name, p, H, W, k) for k in ("ramp", "noise")]
+        e.compute(np.stack([pair[0][0], pair[1][0]]), np.stack([pair[0][1], pair[1][1]]), api.STAGE_BM)
+        out = e.download(2)["disp"]
+        preL, preR = e.debug_read(5, 2), e.debug_read(6, 2)
+        for b, kind in enumerate(("ramp", "noise")):
+            disp, pl, pr = oracle.bm(pair[b][0], pair[b][1], p, want_prefilter=True)
+            check(name + "/preL/" + kind, preL[b], pl)
+            check(name + "/preR/" + kind, preR[b], pr)
+            check(name + "/disp/" + kind, out[b], disp)
+            check(name + "/golden/" + kind, out[b], golden["bm/%s/%s" % (name, kind)])
+
+
+def test_remap_vs_oracle_and_golden(oracle, golden):
+    H, W = 96, 140
+    for seed in range(3):
+        img, img2 = synth.random_pair(H, W, seed=seed)
+        mx, my = cases.warp_maps(H, W, seed)
+        with api.Engine(W, H, max_batch=1) as e:
+            e.upload_rectify_maps(0, mx, my, (0, 0, W, H))
+            e.upload_rectify_maps(1, mx, my, (0, 0, W, H))
+            e.compute(img, img2, api.STAGE_RECTIFY)
+            r = e.download(1, disp=False, rect=True)
+            check("remap/golden/%d" % seed, r["rectL"][0], golden["remap/%d" % seed])
+            check("remap/oracle/%d" % seed, r["rectR"][0], oracle.remap(img2, mx, my))
+        roi = (5, 3, W - 11, H - 9)
+        with api.Engine(W, H, max_batch=1) as e:
+            e.upload_rectify_maps(0, mx, my, roi)
+            e.upload_rectify_maps(1, mx, my, roi)
+            assert (e.info.width, e.info.height) == (W - 11, H - 9)
+            e.compute(img, img2, api.STAGE_RECTIFY)
+            r = e.download(1, disp=False, rect=True)
+            check("remap/crop/%d" % seed, r["rectL"][0], oracle.remap(img, mx, my, roi))
+
+
+def test_strided_roi_views_and_batches(oracle):
+    """cv::Mat ROI views (stride > width, reference src/Stereosystem.cpp:255-256) and batch == per-frame."""
+    name, p, H, W = cases.SGBM_CASES[0]
+    big_l = np.zeros((3, H + 4, W + 24), np.uint8)
+    big_r = np.zeros_like(big_l)
+    frames = []
+    for b in range(3):
+        l, r, _ = synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=40 + b)
+        big_l[b, 2:2 + H, 8:8 + W] = l
+        big_r[b, 2:2 + H, 8:8 + W] = r
+        frames.append((l, r))
+    with api.Engine(W, H, max_batch=3) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(big_l[:, 2:2 + H, 8:8 + W], big_r[:, 2:2 + H, 8:8 + W], api.STAGE_SGBM)
+        out = e.download(3)["disp"]
+        for b in range(3):
+            check("batch/%d" % b, out[b], oracle.sgbm(frames[b][0], frames[b][1], p))
+        # single-frame call through the disparity.h mirror
+        d = api.sgbm(api.Stereopair(frames[1][0], frames[1][1]), e)
+        check("mirror", d, out[1])
+
+
+def test_speckle_median_xyz_means(oracle, golden):
+    """Post-filters on a crafted map are reached through SGBM above; here: consumers on a real SGBM output."""
+    name, p, H, W = cases.SGBM_CASES[0]
+    l, r = cases.sgbm_inputs(name, p, H, W, "ramp")
+    with api.Engine(W, H, max_batch=1) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.set_Q(cases.Q_REFERENCE)
+        off = api.dmap_roi_offset(p["numDisp"], W)
+        rois = api.subimage_rois(W - off, H, off) + api.samplepoint_rois(W - off, H, off)
+        e.set_mean_rois(rois)
+        e.compute(l, r, api.STAGE_SGBM | api.STAGE_XYZ | api.STAGE_MEANS)
+        out = e.download(1, xyz=True, means=True)
+    disp = oracle.sgbm(l, r, p)
+    check("disp", out["disp"][0], disp)
+    xyz, valid = oracle.reproject(disp, cases.Q_REFERENCE)
+    v = valid.astype(bool)
+    assert v.any()
+    np.testing.assert_allclose(out["xyz"][0][v], xyz[v], rtol=1e-5)
+    assert not out["xyz"][0][~v].any()
+    want = np.array([oracle.mean(disp, roi) for roi in rois], np.float32)
+    np.testing.assert_array_equal(out["means"][0], want)      # integer sums + truncating division: exact
+
+
+def test_parameter_contract_rejections():
+    with api.Engine(320, 200) as e:
+        for bad in (dict(numDisp=0), dict(numDisp=20), dict(numDisp=512), dict(numDisp=64, blockSize=21, P2=32 * 441),
+                    dict(numDisp=64, blockSize=5, P2=30000), dict(numDisp=64, preFilterCap=200)):
+            kw = gpu_params(cases.sgbm_params(**bad))
+            with pytest.raises(api.MvsvError) as ex:
+                e.set_sgbm_params(**kw)
+            assert ex.value.code == -1
+        with pytest.raises(api.MvsvError):
+            e.set_bm_params(numDisp=24, blockSize=9, preFilterCap=31, textureThreshold=10, uniquenessRatio=15)
+        l, r = synth.random_pair(200, 320, seed=1)
+        with pytest.raises(api.MvsvError) as ex:
+            e.compute(l, r, api.STAGE_SGBM)                 # params not set
+        assert ex.value.code == -4
+
+
+def test_degenerate_width(oracle):
+    # W1 <= 0: whole map INVALID
+    p = cases.sgbm_params(numDisp=64, blockSize=3)
+    l, r = synth.random_pair(20, 50, seed=3)
+    with api.Engine(50, 20) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(l, r, api.STAGE_SGBM)
+        check("w1<=0", e.download(1)["disp"][0], oracle.sgbm(l, r, p))
+
+
+# ---- BASELINE.json configurations at full size, against cv2 live (cv2 ships in the image) ---------------------
+def _cv2():
+    return pytest.importorskip("cv2")
+
+
+def _cv_sgbm(cv2, l, r, p):
+    m = cv2.StereoSGBM_create(minDisparity=p["minDisp"], numDisparities=p["numDisp"], blockSize=p["blockSize"],
+                              P1=p["P1"], P2=p["P2"], disp12MaxDiff=p["disp12MaxDiff"], preFilterCap=p["preFilterCap"],
+                              uniquenessRatio=p["uniquenessRatio"], speckleWindowSize=p["speckleWindowSize"],
+                              speckleRange=p["speckleRange"],
+                              mode=cv2.STEREO_SGBM_MODE_HH if p["mode"] == 1 else cv2.STEREO_SGBM_MODE_SGBM)
+    return m.compute(l, r)
+
+
+CFG2 = cases.sgbm_params(minDisp=1, numDisp=64, blockSize=13, speckleWindowSize=150, speckleRange=2)
+CFG2_SHIPPED = cases.sgbm_params(minDisp=1, numDisp=128, blockSize=13, speckleWindowSize=150, speckleRange=2)
+CFG4 = cases.sgbm_params(numDisp=256, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, uniquenessRatio=10,
+                         speckleWindowSize=150, speckleRange=2, mode=1)
+CFG5 = cases.sgbm_params(numDisp=256, blockSize=5, P1=200, P2=800)
+
+
+@pytest.mark.parametrize("p,H,W,B", [(CFG2, 480, 752, 4), (CFG2_SHIPPED, 480, 752, 2), (CFG4, 1080, 1920, 1)],
+                         ids=["cfg2_752x480_d64", "sgbm_yml_d128", "cfg4_1080p_d256_hh"])
+def test_full_size_vs_cv2(p, H, W, B):
+    cv2 = _cv2()
+    ls, rs = [], []
+    for b in range(B):
+        l, r, _ = synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=b)
+        ls.append(l); rs.append(r)
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(np.stack(ls), np.stack(rs), api.STAGE_SGBM)
+        out = e.download(B)["disp"]
+    for b in range(B):
+        check("full/%d" % b, out[b], _cv_sgbm(cv2, ls[b], rs[b], p))
+    # the ramp is recovered: median |error| of valid pixels below one disparity step
+    l, r, d = synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=0)
+    valid = out[0] > (p["minDisp"] - 1) * 16
+    err = np.abs(out[0].astype(np.float32) / 16 - d[:, None].astype(np.float32))[valid]
+    assert valid.mean() > 0.5 and np.median(err) < 1.0
+
+
+def test_cfg1_bm_full_size_vs_cv2():
+    cv2 = _cv2()
+    p = dict(numDisp=80, blockSize=21, preFilterCap=2, uniquenessRatio=0, textureThreshold=30)   # configs/bm.yml
+    l, r, _ = synth.stereogram(480, 752, 0, 80, seed=42)
+    m = cv2.StereoBM_create(numDisparities=80, blockSize=21)
+    m.setPreFilterCap(2); m.setUniquenessRatio(0); m.setTextureThreshold(30)
+    with api.Engine(752, 480) as e:
+        e.set_bm_params(**p)
+        d = api.bm(api.Stereopair(l, r), e)
+    check("cfg1", d, m.compute(l, r))
+
+
+def test_cfg3_pipeline(oracle):
+    """remap(maps of parameters/baseline_small) -> crop -> SGBM cfg 2 -> XYZ -> 81 sub-image + sample-point means."""
+    g = np.load(os.path.join(cases.GOLDEN_DIR, "rectify_baseline_small.npz"))
+    roi = tuple(int(v) for v in g["roi"])
+    B = 3
+    raws = [synth.stereogram(480, 752, 1, 64, seed=7 + b)[:2] for b in range(B)]
+    with api.Engine(752, 480, max_batch=B) as e:
+        e.upload_rectify_maps(0, g["m1x"], g["m1y"], roi)
+        e.upload_rectify_maps(1, g["m2x"], g["m2y"], roi)
+        W, H = e.info.width, e.info.height
+        assert (W, H) == (roi[2], roi[3])
+        e.set_sgbm_params(**gpu_params(CFG2))
+        e.set_Q(g["Q"])
+        off = api.dmap_roi_offset(CFG2["numDisp"], W)
+        rois = api.subimage_rois(W - off, H, off) + api.samplepoint_rois(W - off, H, off)
+        e.set_mean_rois(rois)
+        e.compute(np.stack([x[0] for x in raws]), np.stack([x[1] for x in raws]),
+                  api.STAGE_RECTIFY | api.STAGE_SGBM | api.STAGE_XYZ | api.STAGE_MEANS)
+        out = e.download(B, rect=True, xyz=True, means=True)
+    check("rectL/golden", out["rectL"][0], g["rectL"])
+    check("rectR/golden", out["rectR"][0], g["rectR"])
+    for b in range(B):
+        rl = oracle.remap(raws[b][0], g["m1x"], g["m1y"], roi)
+        rr = oracle.remap(raws[b][1], g["m2x"], g["m2y"], roi)
+        check("rectL/%d" % b, out["rectL"][b], rl)
+        check("rectR/%d" % b, out["rectR"][b], rr)
+        disp = oracle.sgbm(rl, rr, CFG2)
+        check("disp/%d" % b, out["disp"][b], disp)
+        xyz, valid = oracle.reproject(disp, g["Q"])
+        v = valid.astype(bool)
+        np.testing.assert_allclose(out["xyz"][b][v], xyz[v], rtol=1e-5)
+        want = np.array([oracle.mean(disp, r_) for r_ in rois], np.float32)
+        np.testing.assert_array_equal(out["means"][b], want)
+
+
+def test_determinism_and_linearity_properties():
+    """Size-independent properties at full size: rerun == same bits; a frame's result does not depend on its
+    batch neighbours; shifting both images by a constant intensity leaves the x-Sobel channel unchanged but not
+    the raw channel, so only idempotence-type properties are asserted."""
+    p, H, W, B = CFG2, 480, 752, 6
+    ls, rs = zip(*[synth.stereogram(H, W, 1, 64, seed=100 + b)[:2] for b in range(B)])
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(np.stack(ls), np.stack(rs), api.STAGE_SGBM)
+        a = e.download(B)["disp"]
+        e.compute(np.stack(ls[::-1]), np.stack(rs[::-1]), api.STAGE_SGBM)
+        b = e.download(B)["disp"]
+        check("permuted batch", b[::-1], a)
+        e.compute(ls[2], rs[2], api.STAGE_SGBM)
+        check("single", e.download(1)["disp"][0], a[2])
