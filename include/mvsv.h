@@ -117,6 +117,16 @@ void* mvsv_stream(mvsv_ctx* ctx);
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 unsigned long long mvsv_launch_count(const mvsv_ctx* ctx);
 
+/* CUDA-event timing on the ctx stream (the stream the kernels are launched on).  timer_start/stop bracket a
+ * region; profile_enable(1) additionally brackets every kernel launch with events, and profile_read returns the
+ * accumulated milliseconds and launch counts per kernel id since the last read (n >= number of kernel ids;
+ * returns that number).  mvsv_kernel_name(id) names an id ("" past the end). */
+int mvsv_timer_start(mvsv_ctx* ctx);
+int mvsv_timer_stop(mvsv_ctx* ctx, float* ms);
+int mvsv_profile_enable(mvsv_ctx* ctx, int enable);
+int mvsv_profile_read(mvsv_ctx* ctx, float* ms, int* counts, int n);
+const char* mvsv_kernel_name(int kid);
+
 /* Pinned host memory for zero-staging async copies. */
 int mvsv_host_alloc(void** p, size_t bytes);
 int mvsv_host_free(void* p);

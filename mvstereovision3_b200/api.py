@@ -19,6 +19,7 @@ ABI_SYMBOLS = (
     "mvsv_upload_rectify_maps", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
     "mvsv_compute_device", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
     "mvsv_host_alloc", "mvsv_host_free", "mvsv_debug_set_flags", "mvsv_debug_read",
+    "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
 )
 
 
@@ -83,6 +84,12 @@ def load_library():
     lib.mvsv_debug_set_flags.argtypes = [vp, C.c_uint]
     lib.mvsv_debug_read.argtypes = [vp, ci, vp, sz]
     lib.mvsv_debug_read.restype = C.c_longlong
+    lib.mvsv_timer_start.argtypes = [vp]
+    lib.mvsv_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.mvsv_profile_enable.argtypes = [vp, ci]
+    lib.mvsv_profile_read.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(ci), ci]
+    lib.mvsv_kernel_name.argtypes = [ci]
+    lib.mvsv_kernel_name.restype = C.c_char_p
     _lib = lib
     return lib
 
@@ -241,6 +248,26 @@ class Engine:
         if means:
             res["means"] = mn
         return res
+
+    # -- timing ---------------------------------------------------------------------------------
+    def timer_start(self):
+        self._ck(self._lib.mvsv_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self._lib.mvsv_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._ck(self._lib.mvsv_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} since the last read (CUDA events on the ctx stream)."""
+        n = 64
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        k = self._ck(self._lib.mvsv_profile_read(self._ctx, ms, cnt, n))
+        return {self._lib.mvsv_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(k) if cnt[i]}
 
     # -- test hooks -----------------------------------------------------------------------------
     def debug_set_flags(self, flags):

@@ -6,6 +6,10 @@
 #include <cstring>
 #include <new>
 
+const char* const kKernelNames[KID_COUNT] = {
+    "remap", "sgbm_prefilter", "sgbm_vsum", "sgbm_h1", "sgbm_vdir", "sgbm_h2_wta", "median3", "ccl_rows", "ccl_vmerge",
+    "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill"};
+
 namespace {
 
 thread_local std::string g_init_error;
@@ -180,8 +184,8 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
         if (rc) return rc;
         rc = upload_images(c, c->raw[1], c->raw_pitch, right, rstride, frame_stride, c->fw, c->fh, batch, device_src);
         if (rc) return rc;
-        c->launches += launch_remap(c, 0, batch);
-        c->launches += launch_remap(c, 1, batch);
+        launch_remap(c, 0, batch);
+        launch_remap(c, 1, batch);
     } else {
         if (lstride < (size_t)c->W || rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "stride smaller than image width");
         rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, c->W, c->H, batch, device_src);
@@ -192,17 +196,17 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
     if (stages & MVSV_STAGE_SGBM) {
         rc = ensure_sgbm_volumes(c);
         if (rc) return rc;
-        c->launches += launch_sgbm(c, batch);
+        launch_sgbm(c, batch);
     } else if (stages & MVSV_STAGE_BM) {
         rc = ensure_bm_volumes(c);
         if (rc) return rc;
-        c->launches += launch_bm(c, batch);
+        launch_bm(c, batch);
     }
     if (stages & MVSV_STAGE_XYZ) {
         if (!c->xyz) MVSV_CK(c, cudaMalloc(&c->xyz, (size_t)c->maxB * c->H * c->W * 3 * sizeof(float)));
-        c->launches += launch_xyz(c, batch);
+        launch_xyz(c, batch);
     }
-    if (stages & MVSV_STAGE_MEANS) c->launches += launch_means(c, batch);
+    if (stages & MVSV_STAGE_MEANS) launch_means(c, batch);
     MVSV_CK(c, cudaGetLastError());
     c->lastB = batch;
     c->last_stages = stages;
@@ -265,6 +269,10 @@ void mvsv_destroy(mvsv_ctx* c)
     free_bm_volumes(c);
     for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); }
     dfree(c->rois);
+    for (auto& b : c->brackets) { cudaEventDestroy(b.a); cudaEventDestroy(b.b); }
+    for (auto e : c->ev_free) cudaEventDestroy(e);
+    if (c->timer_a) cudaEventDestroy(c->timer_a);
+    if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -353,7 +361,7 @@ int mvsv_upload_rectify_maps(mvsv_ctx* c, int cam, const float* mapx, const floa
     e = cudaMemcpy2DAsync(dx, w, mapx, stride_bytes, w, c->fh, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(dy, w, mapy, stride_bytes, w, c->fh, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        c->launches += launch_convert_maps(c, cam, dx, dy, (size_t)c->fw);
+        launch_convert_maps(c, cam, dx, dy, (size_t)c->fw);
         e = cudaStreamSynchronize(c->stream);
     }
     cudaFree(dx); cudaFree(dy);
@@ -474,6 +482,52 @@ int mvsv_host_alloc(void** p, size_t bytes)
     return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? MVSV_OK : MVSV_ERR_NOMEM;
 }
 int mvsv_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? MVSV_OK : MVSV_ERR_CUDA; }
+
+int mvsv_timer_start(mvsv_ctx* c)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!c->timer_a) { MVSV_CK(c, cudaEventCreate(&c->timer_a)); MVSV_CK(c, cudaEventCreate(&c->timer_b)); }
+    MVSV_CK(c, cudaEventRecord(c->timer_a, c->stream));
+    return MVSV_OK;
+}
+
+int mvsv_timer_stop(mvsv_ctx* c, float* ms)
+{
+    if (!c || !ms || !c->timer_a) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    MVSV_CK(c, cudaEventRecord(c->timer_b, c->stream));
+    MVSV_CK(c, cudaEventSynchronize(c->timer_b));
+    MVSV_CK(c, cudaEventElapsedTime(ms, c->timer_a, c->timer_b));
+    return MVSV_OK;
+}
+
+int mvsv_profile_enable(mvsv_ctx* c, int enable)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    c->prof = enable != 0;
+    return MVSV_OK;
+}
+
+int mvsv_profile_read(mvsv_ctx* c, float* ms, int* counts, int n)
+{
+    if (!c || !ms || !counts || n < KID_COUNT) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) { ms[i] = 0.f; counts[i] = 0; }
+    for (auto& b : c->brackets) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, b.a, b.b) == cudaSuccess) { ms[b.kid] += t; counts[b.kid] += 1; }
+        c->ev_free.push_back(b.a); c->ev_free.push_back(b.b);
+    }
+    c->brackets.clear();
+    return KID_COUNT;
+}
+
+const char* mvsv_kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? kKernelNames[kid] : ""; }
 
 int mvsv_debug_set_flags(mvsv_ctx* c, unsigned flags)
 {

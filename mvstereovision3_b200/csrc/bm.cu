@@ -175,39 +175,37 @@ void launch_wta(mvsv_ctx* c, const BmArgs& a, int B)
 
 }  // namespace
 
-int launch_bm(mvsv_ctx* c, int B)
+void launch_bm(mvsv_ctx* c, int B)
 {
     const BmNorm& n = c->bm;
     const int W = c->W, H = c->H;
-    int launches = 0;
     const size_t npx = (size_t)B * W * H;
-    k_fill16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT);
-    ++launches;
+    { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
     {
         dim3 blk(128), grd((W + 127) / 128, H, 2 * B);
+        KernelTimer kt(c, KID_BM_PREFILTER);
         k_bm_prefilter<<<grd, blk, 0, c->stream>>>(c->rect[0], c->rect[1], c->pitch, W, H, n.cap, c->bm_pre[0], c->bm_pre[1]);
-        ++launches;
     }
     const bool any = !(n.lofs >= W || n.width1 < 1) && (H - 2 * n.w2 > 0) && (n.width1 - 2 * n.w2 > 0);
-    if (!any) return launches;
+    if (!any) return;
     {
         dim3 blk(128), grd((W + 127) / 128, H - 2 * n.w2, B);
-        k_bm_tex_col<<<grd, blk, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex);
+        { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_col<<<grd, blk, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex); }
         dim3 grd2((W - 2 * n.w2 + 127) / 128, H - 2 * n.w2, B);
-        k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2);
-        launches += 2;
+        { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2); }
     }
     {
         const int tpb = n.Dp >= 128 ? n.Dp : 128;
         const int xper = tpb / n.Dp;
         dim3 grd((n.width1 + xper - 1) / xper, B);
+        KernelTimer kt(c, KID_BM_COLSUM);
         k_bm_colsum<<<grd, tpb, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.Dp, n.lofs, n.w2,
                                                 c->bm_col);
-        ++launches;
     }
     BmArgs a;
     a.col = c->bm_col; a.tex = c->bm_tex2; a.disp = c->disp; a.W = W; a.H = H; a.width1 = n.width1; a.D = n.D; a.Dp = n.Dp;
     a.lofs = n.lofs; a.w2 = n.w2; a.texThr = n.tex; a.uniq = n.uniq; a.B = B;
+    KernelTimer kt(c, KID_BM_WTA);
     switch (n.G) {
         case 2: launch_wta<2>(c, a, B); break;
         case 4: launch_wta<4>(c, a, B); break;
@@ -215,6 +213,4 @@ int launch_bm(mvsv_ctx* c, int B)
         case 16: launch_wta<16>(c, a, B); break;
         default: launch_wta<32>(c, a, B); break;
     }
-    ++launches;
-    return launches;
 }

@@ -227,59 +227,59 @@ __global__ void k_means(const int16_t* __restrict__ disp, const int* __restrict_
 
 }  // namespace
 
-int launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t strideElems)
+void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t strideElems)
 {
     dim3 blk(128), grd((c->roi[2] + 127) / 128, c->roi[3]);
+    KernelTimer kt(c, KID_REMAP);
     k_convert_maps<<<grd, blk, 0, c->stream>>>(dmapx, dmapy, strideElems, c->roi[0], c->roi[1], c->roi[2], c->roi[3],
                                                c->map_xy[cam]);
-    return 1;
 }
 
-int launch_remap(mvsv_ctx* c, int cam, int B)
+void launch_remap(mvsv_ctx* c, int cam, int B)
 {
     dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    KernelTimer kt(c, KID_REMAP);
     k_remap<<<grd, blk, 0, c->stream>>>(c->raw[cam], c->raw_pitch, c->fw, c->fh, c->map_xy[cam], c->rect[cam], c->pitch,
                                         c->W, c->H);
-    return 1;
 }
 
-int launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
+void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
 {
     dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    KernelTimer kt(c, KID_MEDIAN);
     k_median3<<<grd, blk, 0, c->stream>>>(in, out, c->W, c->H);
-    return 1;
 }
 
-int launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff)
+void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff)
 {
     const int W = c->W, H = c->H;
     const size_t n = (size_t)B * W * H;
     cudaMemsetAsync(c->sizes, 0, n * sizeof(int), c->stream);
     const int nrows = B * H;
-    k_ccl_rows<<<(nrows * 32 + 127) / 128, 128, 0, c->stream>>>(img, c->labels, W, nrows, newVal, maxDiff);
+    { KernelTimer kt(c, KID_CCL_ROWS); k_ccl_rows<<<(nrows * 32 + 127) / 128, 128, 0, c->stream>>>(img, c->labels, W, nrows, newVal, maxDiff); }
     dim3 blk(128), grd((W + 127) / 128, H, B);
     if (H > 1) {
         dim3 grdv((W + 127) / 128, H - 1, B);
+        KernelTimer kt(c, KID_CCL_VMERGE);
         k_ccl_vmerge<<<grdv, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
     }
-    k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff);
-    k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, c->labels, c->sizes, n, newVal, maxSize);
-    return H > 1 ? 4 : 3;
+    { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff); }
+    { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, c->labels, c->sizes, n, newVal, maxSize); }
 }
 
-int launch_xyz(mvsv_ctx* c, int B)
+void launch_xyz(mvsv_ctx* c, int B)
 {
     QMat Q;
     for (int i = 0; i < 16; ++i) Q.q[i] = c->Q[i];
     dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    KernelTimer kt(c, KID_XYZ);
     k_xyz<<<grd, blk, 0, c->stream>>>(c->disp, c->xyz, c->W, c->H, Q);
-    return 1;
 }
 
-int launch_means(mvsv_ctx* c, int B)
+void launch_means(mvsv_ctx* c, int B)
 {
-    if (c->nrois <= 0) return 0;
+    if (c->nrois <= 0) return;
     dim3 grd(c->nrois, B);
+    KernelTimer kt(c, KID_MEANS);
     k_means<<<grd, 128, 0, c->stream>>>(c->disp, c->rois, c->means, c->W, c->H, c->nrois);
-    return 1;
 }

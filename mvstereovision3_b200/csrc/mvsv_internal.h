@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string>
+#include <vector>
 
 #include "../../include/mvsv.h"
 
@@ -24,6 +25,16 @@ struct BmNorm {
     int lofs, width1, FILT;
 };
 
+// kernel ids for the optional per-launch CUDA-event timing (mvsv_profile_*)
+enum KernelId {
+    KID_REMAP = 0, KID_SGBM_PREFILTER, KID_SGBM_VSUM, KID_SGBM_H1, KID_SGBM_VDIR, KID_SGBM_H2_WTA, KID_MEDIAN,
+    KID_CCL_ROWS, KID_CCL_VMERGE, KID_CCL_FLATTEN, KID_CCL_APPLY, KID_BM_PREFILTER, KID_BM_TEX, KID_BM_COLSUM,
+    KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_COUNT
+};
+extern const char* const kKernelNames[KID_COUNT];
+
+struct ProfBracket { int kid; cudaEvent_t a, b; };
+
 struct mvsv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -34,6 +45,10 @@ struct mvsv_ctx {
     unsigned last_stages = 0;
     unsigned long long launches = 0;
     unsigned debug_flags = 0;   // bit0: h2 pass stores the final S volume (test hook)
+    bool prof = false;
+    std::vector<ProfBracket> brackets;      // pending (unread) timed launches
+    std::vector<cudaEvent_t> ev_free;       // recycled events
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     std::string err;
 
     // rectification (device): per camera, fixed-point maps for the ROI only
@@ -82,15 +97,34 @@ struct mvsv_ctx {
     size_t stage_bytes = 0;
 };
 
-// ---- kernel launchers (each returns the number of kernel launches it issued) ------------------------
-int launch_remap(mvsv_ctx* c, int cam, int B);
-int launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t stride_elems);
-int launch_sgbm(mvsv_ctx* c, int B);
-int launch_bm(mvsv_ctx* c, int B);
-int launch_xyz(mvsv_ctx* c, int B);
-int launch_means(mvsv_ctx* c, int B);
-int launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
-int launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff);
+// RAII bracket: records CUDA events on the ctx stream around one kernel launch when profiling is on.
+struct KernelTimer {
+    mvsv_ctx* c; int idx;
+    KernelTimer(mvsv_ctx* ctx, int kid) : c(ctx), idx(-1)
+    {
+        ++c->launches;
+        if (!c->prof) return;
+        ProfBracket b; b.kid = kid;
+        for (cudaEvent_t* e : {&b.a, &b.b}) {
+            if (!c->ev_free.empty()) { *e = c->ev_free.back(); c->ev_free.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(b.a, c->stream);
+        c->brackets.push_back(b);
+        idx = (int)c->brackets.size() - 1;
+    }
+    ~KernelTimer() { if (idx >= 0) cudaEventRecord(c->brackets[idx].b, c->stream); }
+};
+
+// ---- kernel launchers (launch counting happens in KernelTimer) ------------------------------------------
+void launch_remap(mvsv_ctx* c, int cam, int B);
+void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t stride_elems);
+void launch_sgbm(mvsv_ctx* c, int B);
+void launch_bm(mvsv_ctx* c, int B);
+void launch_xyz(mvsv_ctx* c, int B);
+void launch_means(mvsv_ctx* c, int B);
+void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
+void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
 
 #ifdef __CUDACC__

@@ -416,17 +416,16 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
 }
 
 template <int G>
-int launch_sgbm_g(mvsv_ctx* c, int B)
+void launch_sgbm_g(mvsv_ctx* c, int B)
 {
     const SgbmNorm& n = c->sg;
-    int launches = 0;
     cudaStream_t st = c->stream;
     const size_t planeStride = (size_t)c->maxB * c->H * c->pitch;
     {
         dim3 blk(128), grd((c->W + 127) / 128, c->H, 2 * B);
+        KernelTimer kt(c, KID_SGBM_PREFILTER);
         k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->planes[0],
                                               c->planes[1], planeStride);
-        ++launches;
     }
     {
         constexpr int PX = VS_THREADS / G;
@@ -440,8 +439,8 @@ int launch_sgbm_g(mvsv_ctx* c, int B)
         a.NEP = nep; a.nepShift = sh; a.LEN = nep + 8;
         const size_t smem = (size_t)6 * 8 * a.LEN * 2 + (size_t)PX * 12 * 4 + (size_t)(2 * n.SH2 + 1) * VS_THREADS * 16;
         dim3 grd((n.W1 + PX - 1) / PX, B);
+        KernelTimer kt(c, KID_SGBM_VSUM);
         k_sgbm_vsum<G><<<grd, VS_THREADS, smem, st>>>(a);
-        ++launches;
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
@@ -452,17 +451,16 @@ int launch_sgbm_g(mvsv_ctx* c, int B)
     const int TPB = 128;
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
-    k_sgbm_h1<G><<<rowBlocks, TPB, 0, st>>>(a); ++launches;
-    k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 0); ++launches;
-    k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 0); ++launches;
-    k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 0); ++launches;
+    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G><<<rowBlocks, TPB, 0, st>>>(a); }
+    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 0); }
+    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 0); }
+    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 0); }
     if (n.mode == 1) {
-        k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 1); ++launches;
-        k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 1); ++launches;
-        k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 1); ++launches;
+        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 1); }
+        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 1); }
+        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 1); }
     }
-    k_sgbm_h2_wta<G><<<rowBlocks, TPB, 0, st>>>(a); ++launches;
-    return launches;
+    { KernelTimer kt(c, KID_SGBM_H2_WTA); k_sgbm_h2_wta<G><<<rowBlocks, TPB, 0, st>>>(a); }
 }
 
 template <int G>
@@ -485,30 +483,24 @@ cudaError_t sgbm_configure_kernels()
     return cudaSuccess;
 }
 
-int launch_sgbm(mvsv_ctx* c, int B)
+void launch_sgbm(mvsv_ctx* c, int B)
 {
     const SgbmNorm& n = c->sg;
-    int launches = 0;
     const size_t npx = (size_t)B * c->H * c->W;
     if (n.W1 <= 0) {
+        KernelTimer kt(c, KID_FILL);
         k_fill_i16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp_raw, npx, (int16_t)n.INV);
-        ++launches;
     } else {
         switch (n.G) {
-            case 1: launches += launch_sgbm_g<1>(c, B); break;
-            case 2: launches += launch_sgbm_g<2>(c, B); break;
-            case 4: launches += launch_sgbm_g<4>(c, B); break;
-            case 8: launches += launch_sgbm_g<8>(c, B); break;
-            case 16: launches += launch_sgbm_g<16>(c, B); break;
-            default: launches += launch_sgbm_g<32>(c, B); break;
+            case 1: launch_sgbm_g<1>(c, B); break;
+            case 2: launch_sgbm_g<2>(c, B); break;
+            case 4: launch_sgbm_g<4>(c, B); break;
+            case 8: launch_sgbm_g<8>(c, B); break;
+            case 16: launch_sgbm_g<16>(c, B); break;
+            default: launch_sgbm_g<32>(c, B); break;
         }
     }
-    launches += launch_median(c, c->disp_raw, c->disp_med, B);
-    if (n.speckleWin > 0) {
-        cudaMemcpyAsync(c->disp, c->disp_med, npx * sizeof(int16_t), cudaMemcpyDeviceToDevice, c->stream);
-        launches += launch_speckle(c, c->disp, B, n.INV, n.speckleWin, 16 * n.speckleRange);
-    } else {
-        cudaMemcpyAsync(c->disp, c->disp_med, npx * sizeof(int16_t), cudaMemcpyDeviceToDevice, c->stream);
-    }
-    return launches;
+    launch_median(c, c->disp_raw, c->disp_med, B);
+    cudaMemcpyAsync(c->disp, c->disp_med, npx * sizeof(int16_t), cudaMemcpyDeviceToDevice, c->stream);
+    if (n.speckleWin > 0) launch_speckle(c, c->disp, B, n.INV, n.speckleWin, 16 * n.speckleRange);
 }

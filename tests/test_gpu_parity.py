@@ -142,7 +142,7 @@ def test_speckle_median_xyz_means(oracle, golden):
 def test_parameter_contract_rejections():
     with api.Engine(320, 200) as e:
         for bad in (dict(numDisp=0), dict(numDisp=20), dict(numDisp=512), dict(numDisp=64, blockSize=21, P2=32 * 441),
-                    dict(numDisp=64, blockSize=5, P2=30000), dict(numDisp=64, preFilterCap=200)):
+                    dict(numDisp=64, blockSize=5, P2=32000), dict(numDisp=64, preFilterCap=200)):
             kw = gpu_params(cases.sgbm_params(**bad))
             with pytest.raises(api.MvsvError) as ex:
                 e.set_sgbm_params(**kw)
