@@ -269,3 +269,21 @@ def test_determinism_and_linearity_properties():
         check("permuted batch", b[::-1], a)
         e.compute(ls[2], rs[2], api.STAGE_SGBM)
         check("single", e.download(1)["disp"][0], a[2])
+
+
+def test_cpp_mirror_end_to_end(oracle, tmp_path):
+    """C++ host code -> disparity.h mirror -> C ABI -> CUDA, on ROI views with step > cols, against the oracle."""
+    import subprocess
+    from test_host_cpu import _build_shim_demo
+    exe = _build_shim_demo(tmp_path)
+    H, W = 120, 300
+    l, r, _ = synth.stereogram(H, W, 1, 128, seed=9)
+    (tmp_path / "l.raw").write_bytes(l.tobytes())
+    (tmp_path / "r.raw").write_bytes(r.tobytes())
+    yml = tmp_path / "sgbm.yml"     # verbatim reference configs/sgbm.yml
+    yml.write_text("%YAML:1.0\nminDisp: 1\nnumDisp: 128\nblockSize: 13\ndisp12MaxDiff: 0\npreFilterCap: 0\n"
+                   "uniquenessRatio: 0\nspeckleWindowSize: 150\nspeckleWindowRange: 2\nmode: 0\n")
+    subprocess.check_call([exe, str(yml), str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), str(W), str(H),
+                           str(tmp_path / "out.raw")])
+    got = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.int16).reshape(H, W)
+    check("cpp mirror", got, oracle.sgbm(l, r, CFG2_SHIPPED))

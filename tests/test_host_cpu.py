@@ -89,3 +89,19 @@ def test_roi_helpers_follow_reference():
     assert sp[0] == (8 - 2, 8 - 2, 5, 5)
     assert api.dmap_roi_offset(128, 752) == 64
     assert api.dmap_roi_offset(64, 752) == 32
+
+
+def _build_shim_demo(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "shim_demo")
+    libdir = os.path.join(ROOT, "mvstereovision3_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "shim_demo.cpp"), "-o", exe, "-L" + libdir, "-lmvsv",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_mirror_compiles_as_cxx11(tmp_path):
+    """include/mvsv_disparity.hpp (the C++ mirror of reference inc/disparity.h) builds with -std=c++11 like the
+    reference (Makefile:7) and links against libmvsv.so only."""
+    assert os.path.exists(_build_shim_demo(tmp_path))
