@@ -61,6 +61,7 @@ typedef struct mvsv_info {
     int sgbm_minX1, sgbm_W1, sgbm_D, sgbm_Dpad, sgbm_npaths;   /* evaluated cost domain          */
     int num_rois;
     int device;
+    int sgbm_td_cluster;             /* CTAs per frame of the fused previous-row sweep (0: independent passes) */
 } mvsv_info;
 
 /* Create an engine on CUDA device `device` for raw frames of frame_width x frame_height, holding up to
@@ -135,7 +136,8 @@ int mvsv_host_free(void* p);
  * which: 0 = cost volume C, 1 = aggregated S (before the final right-to-left pass), 2 = raw disparity
  * (after LR check, before median), 3 = vertical-sum volume, 4 = disparity after median (before speckle),
  * 5 = BM prefiltered left, 6 = BM prefiltered right.  Returns bytes written or a negative error. */
-/* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1). */
+/* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
+ * bits 8..15: force the cluster size of the fused sweep (1,2,4,8,16; 0xff = force the independent passes). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
 long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
 

@@ -7,7 +7,7 @@
 #include <new>
 
 const char* const kKernelNames[KID_COUNT] = {
-    "remap", "sgbm_prefilter", "sgbm_vsum", "sgbm_h1", "sgbm_vdir", "sgbm_h2_wta", "median3", "ccl_rows", "ccl_vmerge",
+    "remap", "sgbm_prefilter", "sgbm_vsum", "sgbm_h1", "sgbm_vdir", "sgbm_td", "sgbm_h2_wta", "median3", "ccl_rows", "ccl_vmerge",
     "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill"};
 
 namespace {
@@ -40,11 +40,12 @@ int fail(mvsv_ctx* c, int code, const std::string& msg)
 
 void free_images(mvsv_ctx* c)
 {
-    for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->planes[i]); dfree(c->bm_pre[i]); }
+    for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->bm_pre[i]); }
+    dfree(c->recL);
     dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
     dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means);
 }
-void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); c->vol_elems = 0; }
+void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); dfree(c->plR); c->vol_elems = 0; }
 void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
 
 int alloc_images(mvsv_ctx* c)
@@ -54,9 +55,9 @@ int alloc_images(mvsv_ctx* c)
     const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
     for (int i = 0; i < 2; ++i) {
         MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
-        MVSV_CK(c, cudaMalloc(&c->planes[i], 6 * nimg));
         MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg));
     }
+    MVSV_CK(c, cudaMalloc(&c->recL, npx * sizeof(uint2)));
     MVSV_CK(c, cudaMalloc(&c->d2, npx * sizeof(int)));
     MVSV_CK(c, cudaMalloc(&c->disp_raw, npx * sizeof(int16_t)));
     MVSV_CK(c, cudaMalloc(&c->disp_med, npx * sizeof(int16_t)));
@@ -108,13 +109,24 @@ int ensure_sgbm_volumes(mvsv_ctx* c)
 {
     const SgbmNorm& n = c->sg;
     if (n.W1 <= 0) return MVSV_OK;
+    int nv, rp, joff;
+    sgbm_plane_geometry(n, c->W, &nv, &rp, &joff);
     const size_t need = (size_t)c->maxB * c->H * n.W1 * n.Dp;
-    if (need <= c->vol_elems && c->VS) return MVSV_OK;
-    free_sgbm_volumes(c);
-    MVSV_CK(c, cudaMalloc(&c->VS, need * 2));
-    MVSV_CK(c, cudaMalloc(&c->C, need * 2));
-    MVSV_CK(c, cudaMalloc(&c->S, need * 2));
-    c->vol_elems = need;
+    if (!(need <= c->vol_elems && c->VS)) {
+        dfree(c->VS); dfree(c->C); dfree(c->S);
+        c->vol_elems = 0;
+        MVSV_CK(c, cudaMalloc(&c->VS, need * 2));
+        MVSV_CK(c, cudaMalloc(&c->C, need * 2));
+        MVSV_CK(c, cudaMalloc(&c->S, need * 2));
+        c->vol_elems = need;
+    }
+    if (!c->plR || nv != c->vsNV || rp != c->vsRP || joff != c->vsJOFF) {
+        dfree(c->plR);
+        const size_t bytes = (size_t)6 * c->maxB * c->H * rp * sizeof(uint16_t);
+        MVSV_CK(c, cudaMalloc(&c->plR, bytes));
+        MVSV_CK(c, cudaMemsetAsync(c->plR, 0, bytes, c->stream));   // the padding around each row stays zero
+        c->vsNV = nv; c->vsRP = rp; c->vsJOFF = joff;
+    }
     return MVSV_OK;
 }
 
@@ -290,6 +302,7 @@ int mvsv_set_sgbm_params(mvsv_ctx* c, const mvsv_sgbm_params* p)
     if (rc) return rc;
     MVSV_CK(c, cudaStreamSynchronize(c->stream));
     c->sg = n; c->sgbm_raw = *p; c->has_sgbm = true;
+    c->td_nc = sgbm_choose_td_cluster(c);
     return ensure_sgbm_volumes(c);
 }
 
@@ -318,6 +331,7 @@ static int resize_rectified(mvsv_ctx* c, int W, int H)
     if (c->has_sgbm) {
         rc = normalise_sgbm(c, &c->sgbm_raw, &c->sg);
         if (rc) return rc;
+        c->td_nc = sgbm_choose_td_cluster(c);
         rc = ensure_sgbm_volumes(c);
         if (rc) return rc;
     }
@@ -469,7 +483,7 @@ int mvsv_get_info(const mvsv_ctx* c, mvsv_info* info)
         info->sgbm_minX1 = c->sg.minX1; info->sgbm_W1 = c->sg.W1; info->sgbm_D = c->sg.D; info->sgbm_Dpad = c->sg.Dp;
         info->sgbm_npaths = c->sg.npaths;
     }
-    info->num_rois = c->nrois; info->device = c->device;
+    info->num_rois = c->nrois; info->device = c->device; info->sgbm_td_cluster = c->has_sgbm ? c->td_nc : 0;
     return MVSV_OK;
 }
 
@@ -533,6 +547,7 @@ int mvsv_debug_set_flags(mvsv_ctx* c, unsigned flags)
 {
     if (!c) return MVSV_ERR_INVALID;
     c->debug_flags = flags;
+    if (c->has_sgbm) c->td_nc = sgbm_choose_td_cluster(c);
     return MVSV_OK;
 }
 

@@ -27,7 +27,7 @@ struct BmNorm {
 
 // kernel ids for the optional per-launch CUDA-event timing (mvsv_profile_*)
 enum KernelId {
-    KID_REMAP = 0, KID_SGBM_PREFILTER, KID_SGBM_VSUM, KID_SGBM_H1, KID_SGBM_VDIR, KID_SGBM_H2_WTA, KID_MEDIAN,
+    KID_REMAP = 0, KID_SGBM_PREFILTER, KID_SGBM_VSUM, KID_SGBM_H1, KID_SGBM_VDIR, KID_SGBM_TD, KID_SGBM_H2_WTA, KID_MEDIAN,
     KID_CCL_ROWS, KID_CCL_VMERGE, KID_CCL_FLATTEN, KID_CCL_APPLY, KID_BM_PREFILTER, KID_BM_TEX, KID_BM_COLSUM,
     KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_COUNT
 };
@@ -64,10 +64,13 @@ struct mvsv_ctx {
     bool has_sgbm = false, has_bm = false;
     mvsv_sgbm_params sgbm_raw{};
     SgbmNorm sg{};
+    int td_nc = 0;               // cluster size of the fused previous-row sweep (0: independent passes)
     mvsv_bm_params bm_raw{};
     BmNorm bm{};
 
-    uint8_t* planes[2] = {nullptr, nullptr};  // 6 prefilter planes per image: [6][B][H][pitch]
+    uint2* recL = nullptr;                    // left prefilter records [B][H][W] (a_s,lo_s,hi_s,a_r,lo_r,hi_r)
+    uint16_t* plR = nullptr;                  // right prefilter planes, reversed + padded: [6][B][H][vsRP]
+    int vsNV = 0, vsRP = 0, vsJOFF = 0;
     uint16_t* VS = nullptr;                   // [B][H][W1][Dp] vertical box sums of the pixel cost
     uint16_t* C = nullptr;                    // [B][H][W1][Dp] block cost
     uint16_t* S = nullptr;                    // [B][H][W1][Dp] aggregated cost
@@ -126,6 +129,8 @@ void launch_means(mvsv_ctx* c, int B);
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
 void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
+int sgbm_choose_td_cluster(const mvsv_ctx* c);
+void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);
 
 #ifdef __CUDACC__
 // ---- packed 16x2 helpers -----------------------------------------------------------------------------

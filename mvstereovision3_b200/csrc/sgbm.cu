@@ -12,13 +12,20 @@
 // packed 16x2 (VIADD.16x2 / VIMNMX.U16x2 / VIMNMX3 / VIADDMNMX -- the DPX path on sm_100a).
 #include "mvsv_internal.h"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int VS_THREADS = 256;
 
 // ------------------------------------------------------------------------------------------------
-// K2a: prefilter planes (A.2: sob/raw channels with ftzero borders, lo/hi half-sample bounds)
+// K2a: prefilter (A.2: sob/raw channels with ftzero borders, lo/hi half-sample bounds).
+//   right image -> six u16 planes (a_s, lo_s, -hi_s, a_r, lo_r, -hi_r), stored REVERSED in x at index
+//                  j = JOFF + W-1-x of a zero-padded row of RP elements, so that "disparity ascending" is
+//                  "address ascending" and every CTA's first entry is 16-byte aligned;
+//   left image  -> one 8-byte record per pixel (a_s, lo_s, hi_s, a_r, lo_r, hi_r, 0, 0).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int sob_at(const uint8_t* r0, const uint8_t* r1, const uint8_t* r2, int c, int W, int ftzero)
 {
@@ -33,18 +40,18 @@ __device__ __forceinline__ int raw_at(const uint8_t* r1, int c, int W, int ftzer
 }
 
 __global__ void k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch,
-                                 int W, int H, int ftzero, uint8_t* __restrict__ pl0, uint8_t* __restrict__ pl1,
-                                 size_t planeStride)
+                                 int W, int H, int ftzero, uint2* __restrict__ recL, uint16_t* __restrict__ plR,
+                                 size_t planeStrideR, int RP, int JOFF)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
     int f = blockIdx.z >> 1, im = blockIdx.z & 1;
     if (x >= W) return;
     const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
-    uint8_t* pl = (im ? pl1 : pl0) + ((size_t)f * H + y) * pitch + x;
     const uint8_t* r1 = img + (size_t)y * pitch;
     const uint8_t* r0 = img + (size_t)max(y - 1, 0) * pitch;
     const uint8_t* r2 = img + (size_t)min(y + 1, H - 1) * pitch;
+    int v[6];
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
         int a = ch ? raw_at(r1, x, W, ftzero) : sob_at(r0, r1, r2, x, W, ftzero);
@@ -59,22 +66,32 @@ __global__ void k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t
             int m = (a + r) >> 1;
             lo = min(lo, m); hi = max(hi, m);
         }
-        pl[(size_t)(ch * 3 + 0) * planeStride] = (uint8_t)a;
-        pl[(size_t)(ch * 3 + 1) * planeStride] = (uint8_t)lo;
-        pl[(size_t)(ch * 3 + 2) * planeStride] = (uint8_t)hi;
+        v[ch * 3 + 0] = a; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
+    }
+    if (im == 0) {
+        recL[((size_t)f * H + y) * W + x] =
+            make_uint2((unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24),
+                       (unsigned)v[4] | ((unsigned)v[5] << 8));
+    } else {
+        uint16_t* o = plR + ((size_t)f * H + y) * RP + (JOFF + W - 1 - x);
+        o[0 * planeStrideR] = (uint16_t)v[0]; o[1 * planeStrideR] = (uint16_t)v[1]; o[2 * planeStrideR] = (uint16_t)(-v[2]);
+        o[3 * planeStrideR] = (uint16_t)v[3]; o[4 * planeStrideR] = (uint16_t)v[4]; o[5 * planeStrideR] = (uint16_t)(-v[5]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2b: Birchfield-Tomasi pixel cost + vertical box sum.  One CTA = PX = 256/G adjacent columns of one
-// frame, marching down the rows in lock-step; per row the right-image channels of the columns the CTA can
-// touch are staged in shared memory as eight element-shifted copies so that every lane fetches its eight
-// consecutive disparities with one aligned 128-bit load per channel.
+// K2b: Birchfield-Tomasi pixel cost + vertical box sum.  One CTA = PX = 256/G adjacent columns of one frame,
+// marching down the rows in lock-step.  Lane (p, q) evaluates column xa+p at disparities 8q..8q+7: the left
+// pixel is a broadcast scalar, the right pixels are eight consecutive entries of the reversed planes.  Their
+// start is only 2-byte aligned, so each row's entries are staged in shared memory as EIGHT element-shifted copies
+// (built from aligned 128-bit global loads with funnel shifts); every lane then fetches a channel's eight values
+// with one aligned LDS.128 from the copy matching its alignment.  Staging is double buffered (global loads for
+// row t+2 in flight, copies of row t+1 written while row t is consumed): one __syncthreads per row.
 // ------------------------------------------------------------------------------------------------
 struct VsArgs {
-    const uint8_t* plL; const uint8_t* plR; size_t planeStride; size_t pitch;
+    const uint2* recL; const uint16_t* plR; size_t planeStrideR;
     uint16_t* VS;
-    int W, H, W1, D, Dp, minD, minX1, SH2, NEP, LEN, nepShift;
+    int W, H, W1, D, Dp, minD, minX1, SH2, NV, LEN, RP, JOFF;
 };
 
 __device__ __forceinline__ unsigned bt_pair(unsigned v, unsigned v0, unsigned nv1, unsigned uu, unsigned nuu,
@@ -85,14 +102,17 @@ __device__ __forceinline__ unsigned bt_pair(unsigned v, unsigned v0, unsigned nv
     return __vmins2(c0, c1);
 }
 
-template <int G>
+template <int G, bool R8>
 __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
 {
     constexpr int PX = VS_THREADS / G;
+    constexpr int MAXIT = (G == 32 || G == 1) ? 2 : 1;  // staging items (6 arrays x NV vectors, NV <= 64) per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint16_t* sR = reinterpret_cast<uint16_t*>(smem_raw);                        // [6][8][LEN]
-    unsigned* sL = reinterpret_cast<unsigned*>(sR + 6 * 8 * a.LEN);             // [PX][12]
-    uint4* ring = reinterpret_cast<uint4*>(sL + PX * 12);                        // [bs][VS_THREADS]
+    // layout: sR[2 buf][6][8][LEN] u16 | sL[2 buf][PX][12] u32 | ring[bs][VS_THREADS] (uint2 if the pixel cost
+    // fits a byte -- 2*ftzero+63 <= 255 -- else uint4)
+    uint16_t* sR = reinterpret_cast<uint16_t*>(smem_raw);
+    unsigned* sL = reinterpret_cast<unsigned*>(sR + (size_t)2 * 6 * 8 * a.LEN);
+    unsigned char* ring = reinterpret_cast<unsigned char*>(sL + 2 * PX * 12);
 
     const int tid = threadIdx.x;
     const int p = tid / G, q = tid % G;
@@ -102,57 +122,89 @@ __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
     const bool live = (xi < a.W1) && (q * 8 < a.D);
     const int bs = 2 * a.SH2 + 1;
     const int xr_max = xa + PX - 1 + a.minX1 - a.minD;       // entry e <-> right column xr_max - e
+    const int j0 = a.JOFF + a.W - 1 - xr_max;                // reversed-plane index of entry 0 (multiple of 8)
     const int e0 = (PX - 1 - p) + 8 * q;
     const int sh = (-e0) & 7;
-    const int rbase = sh * a.LEN + e0 + sh;                   // + arr*8*LEN
-    const size_t frameOff = (size_t)f * a.H * a.pitch;
+    const int rbase = sh * a.LEN + e0 + sh;                   // + (buf*6 + arr)*8*LEN
+    const int nitems = 6 * a.NV;
+    const int steps = a.H + 2 * a.SH2;
+    const size_t rowsR = (size_t)f * a.H;
+
+    // staging registers: for item (arr, m) the aligned vectors of entries [8m-8, 8m) and [8m, 8m+8)
+    uint4 P[MAXIT], Q[MAXIT];
+    uint2 lrec = make_uint2(0, 0);
+    size_t srcOff[MAXIT]; int dstOff[MAXIT]; bool itemOn[MAXIT];
+#pragma unroll
+    for (int k = 0; k < MAXIT; ++k) {
+        const int item = tid + k * VS_THREADS;
+        itemOn[k] = item < nitems;
+        const int arr = itemOn[k] ? item / a.NV : 0, m = itemOn[k] ? item - arr * a.NV : 0;
+        srcOff[k] = (size_t)arr * a.planeStrideR + rowsR * a.RP + j0 + 8 * m;
+        dstOff[k] = arr * 8 * a.LEN + 8 * m;
+    }
+    auto issue_loads = [&](int t) {
+        const int y = min(max(t - a.SH2, 0), a.H - 1);
+#pragma unroll
+        for (int k = 0; k < MAXIT; ++k) {
+            if (itemOn[k]) {
+                const uint16_t* src = a.plR + srcOff[k] + (size_t)y * a.RP;
+                P[k] = ld128(src - 8);
+                Q[k] = ld128(src);
+            }
+        }
+        if (tid < PX) lrec = (xa + tid < a.W1) ? a.recL[(rowsR + y) * a.W + xa + tid + a.minX1] : make_uint2(0, 0);
+    };
+    auto store_stage = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < MAXIT; ++k) {
+            if (itemOn[k]) {
+                uint16_t* dst = sR + (size_t)buf * 6 * 8 * a.LEN + dstOff[k];
+                const uint4 p4 = P[k], q4 = Q[k];
+                const unsigned f0 = __funnelshift_r(p4.x, p4.y, 16), f1 = __funnelshift_r(p4.y, p4.z, 16);
+                const unsigned f2 = __funnelshift_r(p4.z, p4.w, 16), f3 = __funnelshift_r(p4.w, q4.x, 16);
+                const unsigned f4 = __funnelshift_r(q4.x, q4.y, 16), f5 = __funnelshift_r(q4.y, q4.z, 16);
+                const unsigned f6 = __funnelshift_r(q4.z, q4.w, 16);
+                // copy s holds entry e at position e+s: positions [8m, 8m+8) of copy s = entries [8m-s, 8m-s+8)
+                st128(dst + 0 * a.LEN, q4);
+                st128(dst + 1 * a.LEN, make_uint4(f3, f4, f5, f6));
+                st128(dst + 2 * a.LEN, make_uint4(p4.w, q4.x, q4.y, q4.z));
+                st128(dst + 3 * a.LEN, make_uint4(f2, f3, f4, f5));
+                st128(dst + 4 * a.LEN, make_uint4(p4.z, p4.w, q4.x, q4.y));
+                st128(dst + 5 * a.LEN, make_uint4(f1, f2, f3, f4));
+                st128(dst + 6 * a.LEN, make_uint4(p4.y, p4.z, p4.w, q4.x));
+                st128(dst + 7 * a.LEN, make_uint4(f0, f1, f2, f3));
+            }
+        }
+        if (tid < PX) {
+            // words: 0 uu_s 1 nuu_s 2 uu1_s 3 uu0_s 4 kk_s 5 uu_r 6 nuu_r 7 uu1_r 8 uu0_r 9 kk_r
+            const int us = lrec.x & 0xff, los = (lrec.x >> 8) & 0xff, his = (lrec.x >> 16) & 0xff, ur = lrec.x >> 24;
+            const int lor = lrec.y & 0xff, hir = (lrec.y >> 8) & 0xff;
+            unsigned* d = sL + (buf * PX + tid) * 12;
+            st128(d, make_uint4(pk16(us), pk16(-us), pk16(his), pk16(los)));
+            st128(d + 4, make_uint4(pk16(his - los), pk16(ur), pk16(-ur), pk16(hir)));
+            st128(d + 8, make_uint4(pk16(lor), pk16(hir - lor), 0u, 0u));
+        }
+    };
+
+    issue_loads(0);
+    store_stage(0);
+    if (steps > 1) issue_loads(1);
+    __syncthreads();
 
     uint4 acc = make_uint4(0, 0, 0, 0);
     int slot = 0;
-    const int steps = a.H + 2 * a.SH2;
     for (int t = 0; t < steps; ++t) {
-        const int y = min(max(t - a.SH2, 0), a.H - 1);
-        const size_t rowOff = frameOff + (size_t)y * a.pitch;
-        __syncthreads();
-        // ---- stage right-image channels: pairs of entries, 8 shifted copies, 32-bit stores
-        const int npairs = 6 * (a.NEP >> 1);
-        for (int idx = tid; idx < npairs; idx += VS_THREADS) {
-            const int arr = idx >> (a.nepShift - 1);
-            const int e = (idx & ((a.NEP >> 1) - 1)) << 1;
-            const uint8_t* pl = a.plR + (size_t)arr * a.planeStride + rowOff;
-            const int xr0 = xr_max - e;
-            int vm1 = (xr0 + 1 >= 0 && xr0 + 1 < a.W) ? pl[xr0 + 1] : 0;
-            int v0 = (xr0 >= 0 && xr0 < a.W) ? pl[xr0] : 0;
-            int v1 = (xr0 - 1 >= 0 && xr0 - 1 < a.W) ? pl[xr0 - 1] : 0;
-            if (arr == 2 || arr == 5) { vm1 = -vm1; v0 = -v0; v1 = -v1; }
-            const unsigned we = ((unsigned)v0 & 0xffffu) | ((unsigned)v1 << 16);     // entries (e, e+1)
-            const unsigned wo = ((unsigned)vm1 & 0xffffu) | ((unsigned)v0 << 16);    // entries (e-1, e)
-            unsigned* dst = reinterpret_cast<unsigned*>(sR + (size_t)arr * 8 * a.LEN);
-#pragma unroll
-            for (int s = 0; s < 8; s += 2) {
-                dst[(s * a.LEN + e + s) >> 1] = we;
-                dst[((s + 1) * a.LEN + e + s) >> 1] = wo;      // copy s+1, positions (e+s, e+s+1) = entries (e-1, e)
-            }
+        const int buf = t & 1;
+        if (t + 1 < steps) {
+            store_stage(buf ^ 1);                 // row t+1 (loaded during step t-1)
+            if (t + 2 < steps) issue_loads(t + 2);
         }
-        // ---- stage left-image scalars as packed words
-        for (int sidx = tid; sidx < PX * 12; sidx += VS_THREADS) {
-            const int pp = sidx / 12, w = sidx % 12;
-            unsigned val = 0;
-            if (w < 10 && xa + pp < a.W1) {
-                const int ch = w / 5, k = w % 5;
-                const uint8_t* pl = a.plL + (size_t)(ch * 3) * a.planeStride + rowOff + (xa + pp + a.minX1);
-                const int u = pl[0], lo = pl[a.planeStride], hi = pl[2 * a.planeStride];
-                val = k == 0 ? pk16(u) : k == 1 ? pk16(-u) : k == 2 ? pk16(hi) : k == 3 ? pk16(lo) : pk16(hi - lo);
-            }
-            sL[sidx] = val;
-        }
-        __syncthreads();
         if (live) {
-            const uint4 A0 = ld128(sR + 0 * 8 * a.LEN + rbase), A1 = ld128(sR + 1 * 8 * a.LEN + rbase);
-            const uint4 A2 = ld128(sR + 2 * 8 * a.LEN + rbase), A3 = ld128(sR + 3 * 8 * a.LEN + rbase);
-            const uint4 A4 = ld128(sR + 4 * 8 * a.LEN + rbase), A5 = ld128(sR + 5 * 8 * a.LEN + rbase);
-            const uint4 w0 = ld128(sL + p * 12), w1 = ld128(sL + p * 12 + 4), w2 = ld128(sL + p * 12 + 8);
-            // words: 0 uu_s 1 nuu_s 2 uu1_s 3 uu0_s 4 kk_s 5 uu_r 6 nuu_r 7 uu1_r 8 uu0_r 9 kk_r
+            const uint16_t* rb = sR + (size_t)buf * 6 * 8 * a.LEN + rbase;
+            const uint4 A0 = ld128(rb + 0 * 8 * a.LEN), A1 = ld128(rb + 1 * 8 * a.LEN), A2 = ld128(rb + 2 * 8 * a.LEN);
+            const uint4 A3 = ld128(rb + 3 * 8 * a.LEN), A4 = ld128(rb + 4 * 8 * a.LEN), A5 = ld128(rb + 5 * 8 * a.LEN);
+            const unsigned* lw = sL + (buf * PX + p) * 12;
+            const uint4 w0 = ld128(lw), w1 = ld128(lw + 4), w2 = ld128(lw + 8);
             uint4 pix;
 #define MVSV_PIX(c)                                                                                   \
     {                                                                                                 \
@@ -162,20 +214,28 @@ __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
     }
             MVSV_PIX(x) MVSV_PIX(y) MVSV_PIX(z) MVSV_PIX(w)
 #undef MVSV_PIX
-            uint4* rs = ring + (size_t)slot * VS_THREADS + tid;
-            if (t >= bs) {
-                const uint4 old = *rs;
-                acc.x += pix.x - old.x; acc.y += pix.y - old.y; acc.z += pix.z - old.z; acc.w += pix.w - old.w;
+            uint4 old = make_uint4(0, 0, 0, 0);
+            if (R8) {
+                uint2* rs = reinterpret_cast<uint2*>(ring) + (size_t)slot * VS_THREADS + tid;
+                if (t >= bs) {
+                    const uint2 o = *rs;
+                    old = make_uint4(__byte_perm(o.x, 0, 0x4140), __byte_perm(o.x, 0, 0x4342), __byte_perm(o.y, 0, 0x4140),
+                                     __byte_perm(o.y, 0, 0x4342));
+                }
+                *rs = make_uint2(__byte_perm(pix.x, pix.y, 0x6420), __byte_perm(pix.z, pix.w, 0x6420));
             } else {
-                acc.x += pix.x; acc.y += pix.y; acc.z += pix.z; acc.w += pix.w;
+                uint4* rs = reinterpret_cast<uint4*>(ring) + (size_t)slot * VS_THREADS + tid;
+                if (t >= bs) old = *rs;
+                *rs = pix;
             }
-            *rs = pix;
+            acc.x += pix.x - old.x; acc.y += pix.y - old.y; acc.z += pix.z - old.z; acc.w += pix.w - old.w;
             if (t >= bs - 1) {
                 const int yo = t - (bs - 1);
                 st128(a.VS + (((size_t)f * a.H + yo) * a.W1 + xi) * a.Dp + q * 8, acc);
             }
         }
         if (++slot == bs) slot = 0;
+        __syncthreads();
     }
 }
 
@@ -301,6 +361,123 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
     }
 }
 
+// K3b': the three paths that come from the previous row -- r = (-1,dy), (0,dy), (+1,dy) with dy = -1 (top-down)
+// or +1 (bottom-up, MODE_HH) -- fused: C and S are read once and S written once per sweep (6 B/cell instead of 18).
+// One thread-block CLUSTER per frame; CTA r of the cluster owns the column strip [x0, x1).  The path state of the
+// previous row lives in shared memory: the vertical path at slot lx, the diagonals at the skewed slots
+// (lx -/+ y) mod M, so that a pixel's predecessor sits in the very slot the pixel overwrites (in place, no
+// double buffering, no intra-row hazard).  Only the strip's border columns cross CTAs: they are written into the
+// neighbour's halo through distributed shared memory, and one cluster barrier per row orders everything.
+constexpr int TD_THREADS = 512;
+constexpr int TD_SMEM_LIMIT = 200 * 1024;
+
+struct TdArgs {
+    const uint16_t* C; uint16_t* S;
+    int H, W1, D, Dp, NC, Mmax, bottomUp;
+    unsigned P1P1, P2P2;
+};
+
+__device__ __forceinline__ void ld_state(unsigned (&L)[4], const uint16_t* p)
+{
+    const uint4 v = ld128(p);
+    L[0] = v.x; L[1] = v.y; L[2] = v.z; L[3] = v.w;
+}
+__device__ __forceinline__ void sat_acc(uint4& S, const unsigned (&L)[4])
+{
+    S.x = __viaddmin_u16x2(S.x, L[0], MVSV_PK_MAX); S.y = __viaddmin_u16x2(S.y, L[1], MVSV_PK_MAX);
+    S.z = __viaddmin_u16x2(S.z, L[2], MVSV_PK_MAX); S.w = __viaddmin_u16x2(S.w, L[3], MVSV_PK_MAX);
+}
+
+template <int G>
+__global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: L[3][Mmax][Dp] u16 | halo[2 parity][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[2][2] u32
+    uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* halo = Lb + (size_t)3 * a.Mmax * a.Dp;
+    unsigned* mb = reinterpret_cast<unsigned*>(halo + 4 * a.Dp);
+    unsigned* halom = mb + 3 * a.Mmax;
+
+    const int r = (int)cluster.block_rank();
+    const int f = blockIdx.y;
+    const int x0 = (int)(((long long)a.W1 * r) / a.NC), x1 = (int)(((long long)a.W1 * (r + 1)) / a.NC);
+    const int M = x1 - x0;
+    constexpr int NG = TD_THREADS / G;
+    const int g = threadIdx.x / G, q = threadIdx.x % G;
+    const bool padLane = q * 8 >= a.D;
+    uint16_t* haloR = (r + 1 < a.NC) ? cluster.map_shared_rank(halo, r + 1) : nullptr;   // CTA owning columns x1..
+    uint16_t* haloL = (r > 0) ? cluster.map_shared_rank(halo, r - 1) : nullptr;
+    unsigned* halomR = (r + 1 < a.NC) ? cluster.map_shared_rank(halom, r + 1) : nullptr;
+    unsigned* halomL = (r > 0) ? cluster.map_shared_rank(halom, r - 1) : nullptr;
+    const int iters = (M + NG - 1) / NG;
+    const size_t frameBase = (size_t)f * a.H * a.W1 * a.Dp + q * 8;
+    cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
+
+    int ymod = 0;       // yi mod M
+    for (int yi = 0; yi < a.H; ++yi) {
+        const int y = a.bottomUp ? a.H - 1 - yi : yi;
+        const int par = yi & 1;
+        const size_t rowBase = frameBase + (size_t)y * a.W1 * a.Dp;
+        for (int it = 0; it < iters; ++it) {
+            int lx = g + it * NG;
+            const bool active = lx < M;
+            if (!active) lx = M - 1;
+            const int x = x0 + lx;
+            const size_t off = rowBase + (size_t)x * a.Dp;
+            const uint4 Cc = ld128(a.C + off);
+            uint4 Sc = ld128(a.S + off);
+            unsigned L[4], mm;
+            // ---- vertical path, slot lx
+            {
+                uint16_t* sl = Lb + ((size_t)1 * a.Mmax + lx) * a.Dp + q * 8;
+                if (yi == 0) reset_state(L, mm, padLane);
+                else { ld_state(L, sl); mm = mb[a.Mmax + lx]; }
+                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                if (active) { st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[a.Mmax + lx] = mm; }
+                sat_acc(Sc, L);
+            }
+            // ---- diagonal with predecessor (x-1, previous row): slot (lx - yi) mod M, halo from the left CTA
+            {
+                int s1 = lx - ymod; if (s1 < 0) s1 += M;
+                uint16_t* sl = Lb + ((size_t)0 * a.Mmax + s1) * a.Dp + q * 8;
+                if (yi == 0 || x == 0) reset_state(L, mm, padLane);
+                else if (lx == 0) { ld_state(L, halo + (par * 2 + 0) * a.Dp + q * 8); mm = halom[par * 2 + 0]; }
+                else { ld_state(L, sl); mm = mb[s1]; }
+                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                if (active) {
+                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[s1] = mm;
+                    if (lx == M - 1 && haloR) {
+                        st128(haloR + ((par ^ 1) * 2 + 0) * a.Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
+                        if (q == 0) halomR[(par ^ 1) * 2 + 0] = mm;
+                    }
+                }
+                sat_acc(Sc, L);
+            }
+            // ---- diagonal with predecessor (x+1, previous row): slot (lx + yi) mod M, halo from the right CTA
+            {
+                int s3 = lx + ymod; if (s3 >= M) s3 -= M;
+                uint16_t* sl = Lb + ((size_t)2 * a.Mmax + s3) * a.Dp + q * 8;
+                if (yi == 0 || x == a.W1 - 1) reset_state(L, mm, padLane);
+                else if (lx == M - 1) { ld_state(L, halo + (par * 2 + 1) * a.Dp + q * 8); mm = halom[par * 2 + 1]; }
+                else { ld_state(L, sl); mm = mb[2 * a.Mmax + s3]; }
+                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                if (active) {
+                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[2 * a.Mmax + s3] = mm;
+                    if (lx == 0 && haloL) {
+                        st128(haloL + ((par ^ 1) * 2 + 1) * a.Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
+                        if (q == 0) halomL[(par ^ 1) * 2 + 1] = mm;
+                    }
+                }
+                sat_acc(Sc, L);
+            }
+            if (active) st128(a.S + off, Sc);
+        }
+        if (++ymod == M) ymod = 0;
+        cluster.sync();
+    }
+}
+
 // K3c + K4: right-to-left path r=(+1,0) fused with winner-take-all, uniqueness, sub-pixel interpolation,
 // the disp2 scatter (sequential in x per row, exactly the reference order) and the left-right check.
 __device__ __forceinline__ unsigned pick16(const unsigned (&R)[4], int idx)
@@ -415,32 +592,36 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
+inline size_t td_smem_bytes(int Mmax, int Dp)
+{
+    return (size_t)3 * Mmax * Dp * 2 + (size_t)4 * Dp * 2 + (size_t)3 * Mmax * 4 + 4 * 4 + 16;
+}
+
 template <int G>
 void launch_sgbm_g(mvsv_ctx* c, int B)
 {
     const SgbmNorm& n = c->sg;
     cudaStream_t st = c->stream;
-    const size_t planeStride = (size_t)c->maxB * c->H * c->pitch;
+    const size_t planeStrideR = (size_t)c->maxB * c->H * c->vsRP;
     {
         dim3 blk(128), grd((c->W + 127) / 128, c->H, 2 * B);
         KernelTimer kt(c, KID_SGBM_PREFILTER);
-        k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->planes[0],
-                                              c->planes[1], planeStride);
+        k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->recL, c->plR,
+                                              planeStrideR, c->vsRP, c->vsJOFF);
     }
     {
         constexpr int PX = VS_THREADS / G;
         VsArgs a;
-        a.plL = c->planes[0]; a.plR = c->planes[1]; a.planeStride = planeStride; a.pitch = c->pitch;
+        a.recL = c->recL; a.plR = c->plR; a.planeStrideR = planeStrideR;
         a.VS = c->VS; a.W = c->W; a.H = c->H; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.minD = n.minD; a.minX1 = n.minX1;
-        a.SH2 = n.SH2;
-        const int NE = PX - 1 + n.Dp;
-        int nep = 16, sh = 4;
-        while (nep < NE + 2) { nep <<= 1; ++sh; }
-        a.NEP = nep; a.nepShift = sh; a.LEN = nep + 8;
-        const size_t smem = (size_t)6 * 8 * a.LEN * 2 + (size_t)PX * 12 * 4 + (size_t)(2 * n.SH2 + 1) * VS_THREADS * 16;
+        a.SH2 = n.SH2; a.NV = c->vsNV; a.LEN = 8 * c->vsNV + 8; a.RP = c->vsRP; a.JOFF = c->vsJOFF;
+        const bool r8 = 2 * n.ftzero + 63 <= 255;
+        const size_t smem = (size_t)2 * 6 * 8 * a.LEN * 2 + (size_t)2 * PX * 12 * 4 +
+                            (size_t)(2 * n.SH2 + 1) * VS_THREADS * (r8 ? 8 : 16);
         dim3 grd((n.W1 + PX - 1) / PX, B);
         KernelTimer kt(c, KID_SGBM_VSUM);
-        k_sgbm_vsum<G><<<grd, VS_THREADS, smem, st>>>(a);
+        if (r8) k_sgbm_vsum<G, true><<<grd, VS_THREADS, smem, st>>>(a);
+        else k_sgbm_vsum<G, false><<<grd, VS_THREADS, smem, st>>>(a);
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
@@ -452,21 +633,56 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
     { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G><<<rowBlocks, TPB, 0, st>>>(a); }
-    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 0); }
-    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 0); }
-    { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 0); }
-    if (n.mode == 1) {
-        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, 1); }
-        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, 1); }
-        { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, 1); }
-    }
+    const int nc = c->td_nc;
+    auto vdirs = [&](int bottomUp) {
+        if (nc > 0) {
+            TdArgs t;
+            t.C = c->C; t.S = c->S; t.H = c->H; t.W1 = n.W1; t.D = n.D; t.Dp = n.Dp; t.NC = nc; t.Mmax = (n.W1 + nc - 1) / nc;
+            t.bottomUp = bottomUp; t.P1P1 = a.P1P1; t.P2P2 = a.P2P2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(nc, B, 1); cfg.blockDim = dim3(TD_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = td_smem_bytes(t.Mmax, n.Dp); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            KernelTimer kt(c, KID_SGBM_TD);
+            cudaLaunchKernelEx(&cfg, k_sgbm_td<G>, t);
+        } else {
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, bottomUp); }
+        }
+    };
+    vdirs(0);
+    if (n.mode == 1) vdirs(1);
     { KernelTimer kt(c, KID_SGBM_H2_WTA); k_sgbm_h2_wta<G><<<rowBlocks, TPB, 0, st>>>(a); }
 }
 
 template <int G>
 cudaError_t cfg_vsum()
 {
-    return cudaFuncSetAttribute(k_sgbm_vsum<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_td<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_sgbm_td<G>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
+
+template <int G>
+int td_max_clusters(int nc, size_t smem)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nc, 1, 1); cfg.blockDim = dim3(TD_THREADS, 1, 1); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 }  // namespace
@@ -481,6 +697,48 @@ cudaError_t sgbm_configure_kernels()
     if ((e = cfg_vsum<16>()) != cudaSuccess) return e;
     if ((e = cfg_vsum<32>()) != cudaSuccess) return e;
     return cudaSuccess;
+}
+
+// Cluster size for the fused previous-row sweep: the smallest power of two whose column strip fits in shared
+// memory, raised to 4 when the frame is wide enough (more CTAs per frame = more SMs busy at small batches).
+// 0 = does not fit (or clusters unavailable): fall back to the three independent k_sgbm_vdir passes.
+int sgbm_choose_td_cluster(const mvsv_ctx* c)
+{
+    const SgbmNorm& n = c->sg;
+    if (n.W1 <= 0) return 0;
+    const int forced = (int)((c->debug_flags >> 8) & 0xff);
+    if (forced == 0xff) return 0;
+    for (int nc = 1; nc <= 16; nc <<= 1) {
+        if (forced && nc != forced) continue;
+        if (nc > n.W1) break;
+        const int Mmax = (n.W1 + nc - 1) / nc;
+        const size_t smem = td_smem_bytes(Mmax, n.Dp);
+        if (smem > (size_t)TD_SMEM_LIMIT) continue;
+        if (!forced && nc < 4 && n.W1 >= 4 * 32) continue;
+        int ok = 0;
+        switch (n.G) {
+            case 1: ok = td_max_clusters<1>(nc, smem); break;
+            case 2: ok = td_max_clusters<2>(nc, smem); break;
+            case 4: ok = td_max_clusters<4>(nc, smem); break;
+            case 8: ok = td_max_clusters<8>(nc, smem); break;
+            case 16: ok = td_max_clusters<16>(nc, smem); break;
+            default: ok = td_max_clusters<32>(nc, smem); break;
+        }
+        if (ok > 0) return nc;
+    }
+    return 0;
+}
+
+// Geometry of the reversed right-image planes for the cost kernel (see k_sgbm_prefilter / k_sgbm_vsum).
+void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF)
+{
+    const int PX = VS_THREADS / n.G;
+    const int NE = PX - 1 + n.Dp;                    // entries a CTA can touch
+    int nv = 2;
+    while (nv * 8 < NE + 2) nv <<= 1;                // power of two, one spare vector for the odd copies
+    const int K = W - PX - n.minX1 + n.minD;         // j0 = JOFF + K - xa must be a multiple of 8 (xa is)
+    const int joff = PX + 8 + (((8 - ((PX + 8 + K) % 8)) % 8 + 8) % 8);
+    *NV = nv; *JOFF = joff; *RP = (joff + W + nv * 8 + 16 + 7) / 8 * 8;
 }
 
 void launch_sgbm(mvsv_ctx* c, int B)

@@ -31,6 +31,7 @@ SGBM_CASES = [
     ("d256_hh", sgbm_params(numDisp=256, blockSize=5, P1=200, P2=800, disp12MaxDiff=1, uniquenessRatio=10,
                             speckleWindowSize=50, speckleRange=2, mode=1), 24, 330),
     ("saturated_s", sgbm_params(numDisp=16, blockSize=5, P1=3000, P2=6000, mode=1, preFilterCap=63), 48, 120),
+    ("cap100_wide_cost", sgbm_params(minDisp=2, numDisp=40, blockSize=5, P1=30, P2=200, preFilterCap=100, uniquenessRatio=5), 50, 210),
 ]
 
 # name -> params for the oracle (BmParams of oracle.loader) ; GPU params are the 5 bm.yml-style fields

@@ -55,6 +55,26 @@ def test_sgbm_stages_vs_oracle(oracle, golden, case):
             check(name + "/golden/" + kind, out[b], golden["sgbm/%s/%s" % (name, kind)])
 
 
+@pytest.mark.parametrize("nc", [1, 2, 4, 8, 0xff])
+@pytest.mark.parametrize("ci", [0, 1, 3, 7])
+def test_fused_sweep_cluster_sizes(oracle, ci, nc):
+    """The fused previous-row sweep (thread-block cluster, DSMEM halo exchange) at every cluster size, and the
+    independent-pass fallback (0xff), give the same bits as the oracle (MODE_SGBM and MODE_HH, padded D)."""
+    name, p, H, W = cases.SGBM_CASES[ci]
+    l, r = cases.sgbm_inputs(name, p, H, W, "noise")
+    with api.Engine(W, H, max_batch=2) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.debug_set_flags(1 | (nc << 8))
+        assert e.info.sgbm_td_cluster == (0 if nc == 0xff else nc)
+        e.compute(np.stack([l, l[::-1].copy()]), np.stack([r, r[::-1].copy()]), api.STAGE_SGBM)
+        out = e.download(2)["disp"]
+        Sg = e.debug_read(1, 2)
+    disp, Cv, Sv, rawv = oracle.sgbm(l, r, p, want_volumes=True, want_raw=True)
+    check("S", Sg[0], Sv)
+    check("disp", out[0], disp)
+    check("disp flipped", out[1], oracle.sgbm(l[::-1].copy(), r[::-1].copy(), p))
+
+
 @pytest.mark.parametrize("case", cases.BM_CASES, ids=[c[0] for c in cases.BM_CASES])
 def test_bm_vs_oracle(oracle, golden, case):
     name, p, H, W = case
