@@ -102,6 +102,8 @@ int normalise_sgbm(mvsv_ctx* c, const mvsv_sgbm_params* p, SgbmNorm* n)
         return fail(c, MVSV_ERR_INVALID,
                     "blockSize^2*(2*ftzero+63)+P2 > 32767: int16 overflow regime of OpenCV is outside the bit-exact contract");
     if (n->INV < -32768 || (n->maxD) * 16 > 32767) return fail(c, MVSV_ERR_INVALID, "disparity range does not fit CV_16S");
+    if (n->W1 > 0 && (long long)c->H * n->W1 * n->Dp >= (1ll << 31))
+        return fail(c, MVSV_ERR_UNSUPPORTED, "cost volume of one frame exceeds 2^31 cells");
     return MVSV_OK;
 }
 

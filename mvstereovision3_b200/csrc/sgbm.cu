@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
 // K3: one step of the path recurrence (A.2 `step`) on 8 disparities per lane.
 //   L[k] = C[k] + min(Lp[k], Lp[k-1]+P1, Lp[k+1]+P1, m+P2) - m ;  mm = packed min_k L[k]
 // Off-domain predecessor == state (L = 0, mm = 0), which yields L = C.
+// PAD: numDisp is not 8*G, lanes with q*8 >= D hold the constant 0x7fff (the out-of-range neighbour value).
 // ------------------------------------------------------------------------------------------------
-template <int G>
+template <int G, bool PAD>
 __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const uint4& C, unsigned P1P1, unsigned P2P2,
                                          int q, bool padLane)
 {
@@ -265,7 +266,7 @@ __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const u
     unsigned n1 = __vminu2(__viaddmin_u16x2(__vminu2(X1, X2), P1P1, L[1]), mP2) + C.y - mm;
     unsigned n2 = __vminu2(__viaddmin_u16x2(__vminu2(X2, X3), P1P1, L[2]), mP2) + C.z - mm;
     unsigned n3 = __vminu2(__viaddmin_u16x2(__vminu2(X3, X4), P1P1, L[3]), mP2) + C.w - mm;
-    if (padLane) { n0 = n1 = n2 = n3 = MVSV_PK_MAX; }
+    if (PAD && padLane) { n0 = n1 = n2 = n3 = MVSV_PK_MAX; }
     unsigned m = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G));
@@ -273,11 +274,23 @@ __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const u
     L[0] = n0; L[1] = n1; L[2] = n2; L[3] = n3;
 }
 
+template <bool PAD>
 __device__ __forceinline__ void reset_state(unsigned (&L)[4], unsigned& mm, bool padLane)
 {
-    const unsigned v = padLane ? MVSV_PK_MAX : 0u;
+    const unsigned v = (PAD && padLane) ? MVSV_PK_MAX : 0u;
     L[0] = L[1] = L[2] = L[3] = v;
     mm = 0u;
+}
+
+__device__ __forceinline__ void ld_state(unsigned (&L)[4], const uint16_t* p)
+{
+    const uint4 v = ld128(p);
+    L[0] = v.x; L[1] = v.y; L[2] = v.z; L[3] = v.w;
+}
+__device__ __forceinline__ void sat_acc(uint4& S, const unsigned (&L)[4])
+{
+    S.x = __viaddmin_u16x2(S.x, L[0], MVSV_PK_MAX); S.y = __viaddmin_u16x2(S.y, L[1], MVSV_PK_MAX);
+    S.z = __viaddmin_u16x2(S.z, L[2], MVSV_PK_MAX); S.w = __viaddmin_u16x2(S.w, L[3], MVSV_PK_MAX);
 }
 
 struct AggArgs {
@@ -290,10 +303,13 @@ struct AggArgs {
     int storeS;
 };
 
+constexpr int HPF = 2;      // the row scans keep the loads of the next HPF steps in flight (register prefetch)
+
 // K3a: horizontal box sum (VS -> C) fused with the left-to-right path r=(-1,0).  Writes C and S = L.
-template <int G>
+template <int G, bool PAD>
 __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
 {
+    constexpr int DP = 8 * G;                       // padded disparity count == a.Dp
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nrows = (long long)a.B * a.H;
     long long row = gtid / G;
@@ -301,33 +317,56 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
     const bool active = row < nrows;
     if (!active) row = nrows - 1;
     const bool padLane = q * 8 >= a.D;
-    const size_t rowBase = (size_t)row * a.W1 * a.Dp + q * 8;
-    const uint16_t* vs = a.VS + rowBase;
+    const int W1 = a.W1, SW2 = a.SW2;
+    const size_t rowBase = (size_t)row * W1 * DP + q * 8;
+    const uint16_t* __restrict__ vs = a.VS + rowBase;
+    uint16_t* __restrict__ cp = a.C + rowBase;
+    uint16_t* __restrict__ sp = a.S + rowBase;
 
     uint4 hs = make_uint4(0, 0, 0, 0);
-    for (int j = -a.SW2; j <= a.SW2; ++j) {
-        const uint4 v = ld128(vs + (size_t)min(max(j, 0), a.W1 - 1) * a.Dp);
+    for (int j = -SW2; j <= SW2; ++j) {
+        const uint4 v = ld128(vs + min(max(j, 0), W1 - 1) * DP);
         hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
     }
     unsigned L[4], mm;
-    reset_state(L, mm, padLane);
-    for (int xi = 0; xi < a.W1; ++xi) {
-        const uint4 nx = ld128(vs + (size_t)min(xi + 1 + a.SW2, a.W1 - 1) * a.Dp);
-        const uint4 od = ld128(vs + (size_t)max(xi - a.SW2, 0) * a.Dp);
-        sgm_step<G>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
-        if (active) {
-            st128(a.C + rowBase + (size_t)xi * a.Dp, hs);
-            st128(a.S + rowBase + (size_t)xi * a.Dp, make_uint4(L[0], L[1], L[2], L[3]));
+    reset_state<PAD>(L, mm, padLane);
+    uint4 NX[HPF], OD[HPF];
+#pragma unroll
+    for (int k = 0; k < HPF; ++k) {
+        NX[k] = ld128(vs + min(k + 1 + SW2, W1 - 1) * DP);
+        OD[k] = ld128(vs + max(k - SW2, 0) * DP);
+    }
+    for (int x0 = 0; x0 < W1; x0 += HPF) {
+        uint4 NX2[HPF], OD2[HPF];
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) {
+            const int xn = x0 + HPF + k;
+            NX2[k] = ld128(vs + min(xn + 1 + SW2, W1 - 1) * DP);
+            OD2[k] = ld128(vs + min(max(xn - SW2, 0), W1 - 1) * DP);
         }
-        hs.x += nx.x - od.x; hs.y += nx.y - od.y; hs.z += nx.z - od.z; hs.w += nx.w - od.w;
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) {
+            const int xi = x0 + k;
+            if (xi < W1) {
+                sgm_step<G, PAD>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
+                if (active) {
+                    st128(cp + xi * DP, hs);
+                    st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
+                }
+                hs.x += NX[k].x - OD[k].x; hs.y += NX[k].y - OD[k].y; hs.z += NX[k].z - OD[k].z; hs.w += NX[k].w - OD[k].w;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) { NX[k] = NX2[k]; OD[k] = OD2[k]; }
     }
 }
 
-// K3b: vertical / diagonal paths.  One lane group follows one path line through the frame: the vertical
-// line of column g, or the diagonal that starts at column g and wraps around the cost domain (a wrap is
-// exactly an off-domain predecessor, so the state is reset there).  No inter-thread communication.
+// K3b: vertical / diagonal paths, one direction per launch (generic fallback when the fused sweep below does
+// not fit in shared memory).  One lane group follows one path line through the frame: the vertical line of
+// column g, or the diagonal that starts at column g and wraps around the cost domain (a wrap is exactly an
+// off-domain predecessor, so the state is reset there).  No inter-thread communication.
 //   dxs: x offset of the predecessor (-1, 0, +1);  bottomUp: predecessor row is y+1 instead of y-1.
-template <int G>
+template <int G, bool PAD>
 __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int bottomUp)
 {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,21 +378,19 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
     const int f = (int)(col / a.W1);
     int x = (int)(col % a.W1);
     const bool padLane = q * 8 >= a.D;
-    const size_t frameBase = (size_t)f * a.H * a.W1 * a.Dp + q * 8;
+    constexpr int DP = 8 * G;
+    const size_t frameBase = (size_t)f * a.H * a.W1 * DP + q * 8;
 
     unsigned L[4], mm;
-    reset_state(L, mm, padLane);
+    reset_state<PAD>(L, mm, padLane);
     for (int yi = 0; yi < a.H; ++yi) {
         const int y = bottomUp ? a.H - 1 - yi : yi;
-        const size_t off = frameBase + ((size_t)y * a.W1 + x) * a.Dp;
+        const size_t off = frameBase + ((size_t)y * a.W1 + x) * DP;
         const uint4 Cc = ld128(a.C + off);
         uint4 Sc = ld128(a.S + off);
-        if ((dxs < 0 && x == 0) || (dxs > 0 && x == a.W1 - 1)) reset_state(L, mm, padLane);
-        sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-        Sc.x = __viaddmin_u16x2(Sc.x, L[0], MVSV_PK_MAX);
-        Sc.y = __viaddmin_u16x2(Sc.y, L[1], MVSV_PK_MAX);
-        Sc.z = __viaddmin_u16x2(Sc.z, L[2], MVSV_PK_MAX);
-        Sc.w = __viaddmin_u16x2(Sc.w, L[3], MVSV_PK_MAX);
+        if ((dxs < 0 && x == 0) || (dxs > 0 && x == a.W1 - 1)) reset_state<PAD>(L, mm, padLane);
+        sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+        sat_acc(Sc, L);
         if (active) st128(a.S + off, Sc);
         x -= dxs;
         if (x >= a.W1) x = 0;
@@ -368,6 +405,7 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
 // (lx -/+ y) mod M, so that a pixel's predecessor sits in the very slot the pixel overwrites (in place, no
 // double buffering, no intra-row hazard).  Only the strip's border columns cross CTAs: they are written into the
 // neighbour's halo through distributed shared memory, and one cluster barrier per row orders everything.
+// The C/S vectors of the next work item (also across the row barrier) are prefetched into registers.
 constexpr int TD_THREADS = 512;
 constexpr int TD_SMEM_LIMIT = 200 * 1024;
 
@@ -377,18 +415,7 @@ struct TdArgs {
     unsigned P1P1, P2P2;
 };
 
-__device__ __forceinline__ void ld_state(unsigned (&L)[4], const uint16_t* p)
-{
-    const uint4 v = ld128(p);
-    L[0] = v.x; L[1] = v.y; L[2] = v.z; L[3] = v.w;
-}
-__device__ __forceinline__ void sat_acc(uint4& S, const unsigned (&L)[4])
-{
-    S.x = __viaddmin_u16x2(S.x, L[0], MVSV_PK_MAX); S.y = __viaddmin_u16x2(S.y, L[1], MVSV_PK_MAX);
-    S.z = __viaddmin_u16x2(S.z, L[2], MVSV_PK_MAX); S.w = __viaddmin_u16x2(S.w, L[3], MVSV_PK_MAX);
-}
-
-template <int G>
+template <int G, bool PAD>
 __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -411,44 +438,62 @@ __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
     unsigned* halomR = (r + 1 < a.NC) ? cluster.map_shared_rank(halom, r + 1) : nullptr;
     unsigned* halomL = (r > 0) ? cluster.map_shared_rank(halom, r - 1) : nullptr;
     const int iters = (M + NG - 1) / NG;
-    const size_t frameBase = (size_t)f * a.H * a.W1 * a.Dp + q * 8;
+    constexpr int Dp = 8 * G;                       // == a.Dp
+    const int Mmax = a.Mmax, W1 = a.W1;
+    const int rowElems = W1 * Dp;
+    // per-thread base pointers; all further offsets are 32-bit element counts
+    const uint16_t* __restrict__ cbase = a.C + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
+    uint16_t* __restrict__ sbase = a.S + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
+    const int rowStep = a.bottomUp ? -rowElems : rowElems;
+    uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
+    uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
+    uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
     cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
 
+    // work item (yi, it): pixel lx = g + it*NG of row yi; its C/S are loaded one item ahead
+    const int lxFirst = min(g, M - 1);
+    uint4 Cn = ld128(cbase + lxFirst * Dp), Sn = ld128(sbase + lxFirst * Dp);
     int ymod = 0;       // yi mod M
+    int rowOff = 0;     // yi * rowStep (fits 32 bit: H*W1*Dp < 2^31 is checked on the host)
     for (int yi = 0; yi < a.H; ++yi) {
-        const int y = a.bottomUp ? a.H - 1 - yi : yi;
         const int par = yi & 1;
-        const size_t rowBase = frameBase + (size_t)y * a.W1 * a.Dp;
+        const bool firstRow = yi == 0;
         for (int it = 0; it < iters; ++it) {
             int lx = g + it * NG;
             const bool active = lx < M;
             if (!active) lx = M - 1;
             const int x = x0 + lx;
-            const size_t off = rowBase + (size_t)x * a.Dp;
-            const uint4 Cc = ld128(a.C + off);
-            uint4 Sc = ld128(a.S + off);
+            const int off = rowOff + lx * Dp;
+            const uint4 Cc = Cn;
+            uint4 Sc = Sn;
+            {
+                const bool lastIt = it + 1 == iters;
+                const int nlx = min(lastIt ? g : g + (it + 1) * NG, M - 1);
+                const int noff = (lastIt ? rowOff + rowStep : rowOff) + nlx * Dp;
+                if (!(lastIt && yi + 1 == a.H)) { Cn = ld128(cbase + noff); Sn = ld128(sbase + noff); }
+            }
             unsigned L[4], mm;
             // ---- vertical path, slot lx
             {
-                uint16_t* sl = Lb + ((size_t)1 * a.Mmax + lx) * a.Dp + q * 8;
-                if (yi == 0) reset_state(L, mm, padLane);
-                else { ld_state(L, sl); mm = mb[a.Mmax + lx]; }
-                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-                if (active) { st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[a.Mmax + lx] = mm; }
+                uint16_t* sl = L1b + lx * Dp;
+                if (firstRow) reset_state<PAD>(L, mm, padLane);
+                else { ld_state(L, sl); mm = mb[Mmax + lx]; }
+                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                if (active) { st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[Mmax + lx] = mm; }
                 sat_acc(Sc, L);
             }
             // ---- diagonal with predecessor (x-1, previous row): slot (lx - yi) mod M, halo from the left CTA
             {
                 int s1 = lx - ymod; if (s1 < 0) s1 += M;
-                uint16_t* sl = Lb + ((size_t)0 * a.Mmax + s1) * a.Dp + q * 8;
-                if (yi == 0 || x == 0) reset_state(L, mm, padLane);
-                else if (lx == 0) { ld_state(L, halo + (par * 2 + 0) * a.Dp + q * 8); mm = halom[par * 2 + 0]; }
+                uint16_t* sl = L0b + s1 * Dp;
+                if (firstRow || x == 0) reset_state<PAD>(L, mm, padLane);
+                else if (lx == 0) { ld_state(L, halo + (par * 2 + 0) * Dp + q * 8); mm = halom[par * 2 + 0]; }
                 else { ld_state(L, sl); mm = mb[s1]; }
-                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
                 if (active) {
                     st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[s1] = mm;
                     if (lx == M - 1 && haloR) {
-                        st128(haloR + ((par ^ 1) * 2 + 0) * a.Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
+                        st128(haloR + ((par ^ 1) * 2 + 0) * Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
                         if (q == 0) halomR[(par ^ 1) * 2 + 0] = mm;
                     }
                 }
@@ -457,23 +502,24 @@ __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
             // ---- diagonal with predecessor (x+1, previous row): slot (lx + yi) mod M, halo from the right CTA
             {
                 int s3 = lx + ymod; if (s3 >= M) s3 -= M;
-                uint16_t* sl = Lb + ((size_t)2 * a.Mmax + s3) * a.Dp + q * 8;
-                if (yi == 0 || x == a.W1 - 1) reset_state(L, mm, padLane);
-                else if (lx == M - 1) { ld_state(L, halo + (par * 2 + 1) * a.Dp + q * 8); mm = halom[par * 2 + 1]; }
-                else { ld_state(L, sl); mm = mb[2 * a.Mmax + s3]; }
-                sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
+                uint16_t* sl = L2b + s3 * Dp;
+                if (firstRow || x == W1 - 1) reset_state<PAD>(L, mm, padLane);
+                else if (lx == M - 1) { ld_state(L, halo + (par * 2 + 1) * Dp + q * 8); mm = halom[par * 2 + 1]; }
+                else { ld_state(L, sl); mm = mb[2 * Mmax + s3]; }
+                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
                 if (active) {
-                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[2 * a.Mmax + s3] = mm;
+                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[2 * Mmax + s3] = mm;
                     if (lx == 0 && haloL) {
-                        st128(haloL + ((par ^ 1) * 2 + 1) * a.Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
+                        st128(haloL + ((par ^ 1) * 2 + 1) * Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
                         if (q == 0) halomL[(par ^ 1) * 2 + 1] = mm;
                     }
                 }
                 sat_acc(Sc, L);
             }
-            if (active) st128(a.S + off, Sc);
+            if (active) st128(sbase + off, Sc);
         }
         if (++ymod == M) ymod = 0;
+        rowOff += rowStep;
         cluster.sync();
     }
 }
@@ -482,9 +528,9 @@ __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
 // the disp2 scatter (sequential in x per row, exactly the reference order) and the left-right check.
 __device__ __forceinline__ unsigned pick16(const unsigned (&R)[4], int idx)
 {
-    const int w = (idx >> 1) & 3;
-    unsigned r = w == 0 ? R[0] : w == 1 ? R[1] : w == 2 ? R[2] : R[3];
-    return (idx & 1) ? (r >> 16) : (r & 0xffffu);
+    const unsigned lo = (idx & 2) ? R[1] : R[0], hi = (idx & 2) ? R[3] : R[2];
+    const unsigned r = (idx & 4) ? hi : lo;
+    return __byte_perm(r, 0, (idx & 1) ? 0x4432 : 0x4410);
 }
 
 template <int G>
@@ -495,7 +541,17 @@ __device__ __forceinline__ bool group_any(bool v)
     return (b & gmask) != 0u;
 }
 
-template <int G>
+// trunc(n / d) for |n| < 2^22, 0 < d < 2^20: float reciprocal estimate plus an exact two-sided correction
+__device__ __forceinline__ int div_trunc_small(int n, int d)
+{
+    const int an = abs(n);
+    int qq = __float2int_rz(__fdividef((float)an, (float)d));
+    const int rem = an - qq * d;
+    qq += (rem >= d) - (rem < 0);
+    return n < 0 ? -qq : qq;
+}
+
+template <int G, bool PAD>
 __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
 {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,72 +561,88 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     const bool active = row < nrows;
     if (!active) row = nrows - 1;
     const bool padLane = q * 8 >= a.D;
-    const size_t rowBase = (size_t)row * a.W1 * a.Dp + q * 8;
-    int16_t* drow = a.disp + (size_t)row * a.W;
-    int* d2row = a.d2 + (size_t)row * a.W;
+    constexpr int Dp = 8 * G;                       // == a.Dp
+    const int W1 = a.W1;
+    const size_t rowBase = (size_t)row * W1 * Dp + q * 8;
+    const uint16_t* __restrict__ cp = a.C + rowBase;
+    uint16_t* __restrict__ sp = a.S + rowBase;
+    int16_t* __restrict__ drow = a.disp + (size_t)row * a.W;
+    int* __restrict__ d2row = a.d2 + (size_t)row * a.W;
     const int d2init = (MVSV_MAX_COST << 16) | (a.INV & 0xffff);
     if (active)
         for (int x = q; x < a.W; x += G) { drow[x] = (int16_t)a.INV; d2row[x] = d2init; }
     __syncwarp();
 
     unsigned L[4], mm;
-    reset_state(L, mm, padLane);
+    reset_state<PAD>(L, mm, padLane);
     const int umul = 100 - a.uniq;
-    for (int xi = a.W1 - 1; xi >= 0; --xi) {
-        const size_t off = rowBase + (size_t)xi * a.Dp;
-        const uint4 Cc = ld128(a.C + off);
-        const uint4 Sc = ld128(a.S + off);
-        sgm_step<G>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-        unsigned Sf[4];
-        Sf[0] = __viaddmin_u16x2(Sc.x, L[0], MVSV_PK_MAX);
-        Sf[1] = __viaddmin_u16x2(Sc.y, L[1], MVSV_PK_MAX);
-        Sf[2] = __viaddmin_u16x2(Sc.z, L[2], MVSV_PK_MAX);
-        Sf[3] = __viaddmin_u16x2(Sc.w, L[3], MVSV_PK_MAX);
-        if (padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
-        if (a.storeS && active) st128(a.S + off, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
-        // ---- first argmin via (S << 16 | k) keys
-        const unsigned kb = (unsigned)q * 8u;
-        unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
-                           min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
-        key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
-                           min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
+    const unsigned kb = (unsigned)q * 8u;
+    uint4 CQ[HPF], SQ[HPF];
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
-        const int minS = (int)(key >> 16);
-        const int best = (int)(key & 0xffffu);
-        bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
-        if (a.uniq > 0) {
-            bool bad = false;
+    for (int k = 0; k < HPF; ++k) {
+        const int xi = max(W1 - 1 - k, 0);
+        CQ[k] = ld128(cp + xi * Dp); SQ[k] = ld128(sp + xi * Dp);
+    }
+    for (int x0 = W1 - 1; x0 >= 0; x0 -= HPF) {
+        uint4 CQ2[HPF], SQ2[HPF];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = (int)kb + j;
-                const int s = (int)pick16(Sf, j);
-                bad |= (k < a.D) && (s * umul < minS * 100) && (abs(k - best) > 1);
-            }
-            reject |= group_any<G>(bad);
+        for (int k = 0; k < HPF; ++k) {
+            const int xn = max(x0 - HPF - k, 0);
+            CQ2[k] = ld128(cp + xn * Dp); SQ2[k] = ld128(sp + xn * Dp);
         }
-        // ---- neighbours of the winner for the parabola
-        int sm1 = 0, sp1 = 0;
-        {
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) {
+            const int xi = x0 - k;
+            if (xi < 0) continue;
+            sgm_step<G, PAD>(L, mm, CQ[k], a.P1P1, a.P2P2, q, padLane);
+            unsigned Sf[4];
+            Sf[0] = __viaddmin_u16x2(SQ[k].x, L[0], MVSV_PK_MAX);
+            Sf[1] = __viaddmin_u16x2(SQ[k].y, L[1], MVSV_PK_MAX);
+            Sf[2] = __viaddmin_u16x2(SQ[k].z, L[2], MVSV_PK_MAX);
+            Sf[3] = __viaddmin_u16x2(SQ[k].w, L[3], MVSV_PK_MAX);
+            if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
+            if (a.storeS && active) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
+            // ---- first argmin via (S << 16 | k) keys
+            unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
+                               min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
+            key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
+                               min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
+            const int minS = (int)(key >> 16);
+            const int best = (int)(key & 0xffffu);
+            bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
+            if (a.uniq > 0) {
+                bool bad = false;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kk = (int)kb + j;
+                    const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
+                    bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
+                }
+                reject |= group_any<G>(bad);
+            }
+            // ---- neighbours of the winner for the parabola
             const int im = max(best - 1, 0), ip = min(best + 1, a.D - 1);
             unsigned vm = pick16(Sf, im & 7), vp = pick16(Sf, ip & 7);
             if (G > 1) {
                 vm = __shfl_sync(FULL, vm, im >> 3, G);
                 vp = __shfl_sync(FULL, vp, ip >> 3, G);
             }
-            sm1 = (int)vm; sp1 = (int)vp;
-        }
-        if (active && q == 0 && !reject) {
-            const int x2 = xi + a.minX1 - best - a.minD;
-            const int cur = d2row[x2];
-            if ((cur >> 16) > minS) d2row[x2] = (minS << 16) | ((best + a.minD) & 0xffff);
+            const int sm1 = (int)vm, sp1 = (int)vp;
             int v = 16 * best;
             if (best > 0 && best < a.D - 1) {
                 const int den = max(sm1 + sp1 - 2 * minS, 1);
-                v += ((sm1 - sp1) * 16 + den) / (2 * den);
+                v += div_trunc_small((sm1 - sp1) * 16 + den, 2 * den);
             }
-            drow[xi + a.minX1] = (int16_t)(v + 16 * a.minD);
+            if (active && q == 0 && !reject) {
+                int* dp = d2row + (xi + a.minX1 - best - a.minD);
+                if ((*dp >> 16) > minS) *dp = (minS << 16) | ((best + a.minD) & 0xffff);
+                drow[xi + a.minX1] = (int16_t)(v + 16 * a.minD);
+            }
         }
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) { CQ[k] = CQ2[k]; SQ[k] = SQ2[k]; }
     }
     __syncwarp();
     if (active) {
@@ -597,7 +669,7 @@ inline size_t td_smem_bytes(int Mmax, int Dp)
     return (size_t)3 * Mmax * Dp * 2 + (size_t)4 * Dp * 2 + (size_t)3 * Mmax * 4 + 4 * 4 + 16;
 }
 
-template <int G>
+template <int G, bool PAD>
 void launch_sgbm_g(mvsv_ctx* c, int B)
 {
     const SgbmNorm& n = c->sg;
@@ -632,7 +704,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const int TPB = 128;
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
-    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G><<<rowBlocks, TPB, 0, st>>>(a); }
+    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, 0, st>>>(a); }
     const int nc = c->td_nc;
     auto vdirs = [&](int bottomUp) {
         if (nc > 0) {
@@ -647,16 +719,16 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
             at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             KernelTimer kt(c, KID_SGBM_TD);
-            cudaLaunchKernelEx(&cfg, k_sgbm_td<G>, t);
+            cudaLaunchKernelEx(&cfg, k_sgbm_td<G, PAD>, t);
         } else {
-            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
-            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
-            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G><<<colBlocks, TPB, 0, st>>>(a, +1, bottomUp); }
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
+            { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, +1, bottomUp); }
         }
     };
     vdirs(0);
     if (n.mode == 1) vdirs(1);
-    { KernelTimer kt(c, KID_SGBM_H2_WTA); k_sgbm_h2_wta<G><<<rowBlocks, TPB, 0, st>>>(a); }
+    { KernelTimer kt(c, KID_SGBM_H2_WTA); k_sgbm_h2_wta<G, PAD><<<rowBlocks, TPB, 0, st>>>(a); }
 }
 
 template <int G>
@@ -666,9 +738,13 @@ cudaError_t cfg_vsum()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_vsum<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_td<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
+    e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_sgbm_td<G>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 
 template <int G>
@@ -681,7 +757,7 @@ int td_max_clusters(int nc, size_t smem)
     at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -749,13 +825,14 @@ void launch_sgbm(mvsv_ctx* c, int B)
         KernelTimer kt(c, KID_FILL);
         k_fill_i16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp_raw, npx, (int16_t)n.INV);
     } else {
+        const bool pad = n.D != n.Dp;
         switch (n.G) {
-            case 1: launch_sgbm_g<1>(c, B); break;
-            case 2: launch_sgbm_g<2>(c, B); break;
-            case 4: launch_sgbm_g<4>(c, B); break;
-            case 8: launch_sgbm_g<8>(c, B); break;
-            case 16: launch_sgbm_g<16>(c, B); break;
-            default: launch_sgbm_g<32>(c, B); break;
+            case 1: if (pad) launch_sgbm_g<1, true>(c, B); else launch_sgbm_g<1, false>(c, B); break;
+            case 2: if (pad) launch_sgbm_g<2, true>(c, B); else launch_sgbm_g<2, false>(c, B); break;
+            case 4: if (pad) launch_sgbm_g<4, true>(c, B); else launch_sgbm_g<4, false>(c, B); break;
+            case 8: if (pad) launch_sgbm_g<8, true>(c, B); else launch_sgbm_g<8, false>(c, B); break;
+            case 16: if (pad) launch_sgbm_g<16, true>(c, B); else launch_sgbm_g<16, false>(c, B); break;
+            default: if (pad) launch_sgbm_g<32, true>(c, B); else launch_sgbm_g<32, false>(c, B); break;
         }
     }
     launch_median(c, c->disp_raw, c->disp_med, B);
