@@ -139,6 +139,20 @@ __global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ 
     ccl_unite(label, label[i], label[u]);
 }
 
+// phase 1: only the run starts (the union-find tree nodes) chase their root and point straight at it
+__global__ void k_ccl_flatten_starts(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int newVal,
+                                     int maxDiff)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
+    const int l = label[i];
+    if (l < 0) return;
+    const bool runStart = (x == 0) || !conn(img[i], img[i - 1], newVal, maxDiff);
+    if (runStart && l != (int)i) label[i] = ccl_find(label, l);     // monotone: always an ancestor, races are benign
+}
+
+// phase 2: every pixel is now at most two hops from its root; the last pixel of each run adds the run length
 __global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ sizes, int W,
                               int H, int newVal, int maxDiff)
 {
@@ -148,15 +162,14 @@ __global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__
     const size_t i = rowBase + x;
     const int l = label[i];
     if (l < 0) return;
-    const int root = ccl_find(label, l);
     const int v = img[i];
     const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
     const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
-    // labels of run starts are union-find tree links (compressing them towards the root is safe);
-    // labels of the other pixels still hold their run start, which gives the run length.
-    const int xs = runStart ? x : (l - (int)rowBase);
-    label[i] = root;
-    if (runEnd) atomicAdd(&sizes[root], x - xs + 1);
+    if (!runEnd) return;
+    // label of a run start = tree link (root after phase 1, or itself); label of other pixels = their run start
+    const int start = runStart ? (int)i : l;
+    const int root = ccl_find(label, start);
+    atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
 }
 
 __global__ void k_ccl_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ sizes,
@@ -166,7 +179,7 @@ __global__ void k_ccl_apply(int16_t* __restrict__ img, const int* __restrict__ l
     if (i >= n) return;
     const int l = label[i];
     if (l < 0) return;
-    const int root = ccl_find(label, l);
+    const int root = ccl_find(label, l);          // <= 2 hops after k_ccl_flatten_starts
     if (sizes[root] <= maxSize) img[i] = (int16_t)newVal;
 }
 
@@ -263,6 +276,7 @@ void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, i
         KernelTimer kt(c, KID_CCL_VMERGE);
         k_ccl_vmerge<<<grdv, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
     }
+    { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten_starts<<<grd, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff); }
     { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff); }
     { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, c->labels, c->sizes, n, newVal, maxSize); }
 }

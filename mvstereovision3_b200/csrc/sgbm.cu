@@ -43,31 +43,28 @@ __global__ void k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t
                                  int W, int H, int ftzero, uint2* __restrict__ recL, uint16_t* __restrict__ plR,
                                  size_t planeStrideR, int RP, int JOFF)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    int f = blockIdx.z >> 1, im = blockIdx.z & 1;
-    if (x >= W) return;
+    // 30 output columns per warp: lanes 0 and 31 only supply the neighbours of lanes 1 and 30
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = (blockIdx.x * (blockDim.x >> 5) + warp) * 30 + lane - 1;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
     const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
     const uint8_t* r1 = img + (size_t)y * pitch;
     const uint8_t* r0 = img + (size_t)max(y - 1, 0) * pitch;
     const uint8_t* r2 = img + (size_t)min(y + 1, H - 1) * pitch;
+    const bool inimg = x >= 0 && x < W;
+    int a[2] = {0, 0};
+    if (inimg) { a[0] = sob_at(r0, r1, r2, x, W, ftzero); a[1] = raw_at(r1, x, W, ftzero); }
     int v[6];
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-        int a = ch ? raw_at(r1, x, W, ftzero) : sob_at(r0, r1, r2, x, W, ftzero);
-        int lo = a, hi = a;
-        if (x > 0) {
-            int l = ch ? raw_at(r1, x - 1, W, ftzero) : sob_at(r0, r1, r2, x - 1, W, ftzero);
-            int m = (a + l) >> 1;
-            lo = min(lo, m); hi = max(hi, m);
-        }
-        if (x < W - 1) {
-            int r = ch ? raw_at(r1, x + 1, W, ftzero) : sob_at(r0, r1, r2, x + 1, W, ftzero);
-            int m = (a + r) >> 1;
-            lo = min(lo, m); hi = max(hi, m);
-        }
-        v[ch * 3 + 0] = a; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
+        const int l = __shfl_up_sync(0xffffffffu, a[ch], 1), r = __shfl_down_sync(0xffffffffu, a[ch], 1);
+        int lo = a[ch], hi = a[ch];
+        if (x > 0) { const int m = (a[ch] + l) >> 1; lo = min(lo, m); hi = max(hi, m); }
+        if (x < W - 1) { const int m = (a[ch] + r) >> 1; lo = min(lo, m); hi = max(hi, m); }
+        v[ch * 3 + 0] = a[ch]; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
     }
+    if (!inimg || lane == 0 || lane == 31) return;
     if (im == 0) {
         recL[((size_t)f * H + y) * W + x] =
             make_uint2((unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24),
@@ -323,41 +320,43 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
     uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
 
+    // ring[s][thread]: the vector that leaves the window at step xi was the entering one bs steps earlier
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw) + threadIdx.x;
+    const int bs = 2 * SW2 + 1;
     uint4 hs = make_uint4(0, 0, 0, 0);
     for (int j = -SW2; j <= SW2; ++j) {
         const uint4 v = ld128(vs + min(max(j, 0), W1 - 1) * DP);
         hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
+        ring[(j + SW2) * 128] = v;                  // slot of step xi = j + SW2 holds VS[max(xi - SW2, 0)]
     }
     unsigned L[4], mm;
     reset_state<PAD>(L, mm, padLane);
-    uint4 NX[HPF], OD[HPF];
+    uint4 NX[HPF];
 #pragma unroll
-    for (int k = 0; k < HPF; ++k) {
-        NX[k] = ld128(vs + min(k + 1 + SW2, W1 - 1) * DP);
-        OD[k] = ld128(vs + max(k - SW2, 0) * DP);
-    }
+    for (int k = 0; k < HPF; ++k) NX[k] = ld128(vs + min(k + 1 + SW2, W1 - 1) * DP);
+    int slot = 0;
     for (int x0 = 0; x0 < W1; x0 += HPF) {
-        uint4 NX2[HPF], OD2[HPF];
+        uint4 NX2[HPF];
 #pragma unroll
-        for (int k = 0; k < HPF; ++k) {
-            const int xn = x0 + HPF + k;
-            NX2[k] = ld128(vs + min(xn + 1 + SW2, W1 - 1) * DP);
-            OD2[k] = ld128(vs + min(max(xn - SW2, 0), W1 - 1) * DP);
-        }
+        for (int k = 0; k < HPF; ++k) NX2[k] = ld128(vs + min(x0 + HPF + k + 1 + SW2, W1 - 1) * DP);
 #pragma unroll
         for (int k = 0; k < HPF; ++k) {
             const int xi = x0 + k;
             if (xi < W1) {
+                const uint4 od = ring[slot * 128];
+                ring[slot * 128] = NX[k];
+                if (++slot == bs) slot = 0;
                 sgm_step<G, PAD>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
                 if (active) {
                     st128(cp + xi * DP, hs);
                     st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
                 }
-                hs.x += NX[k].x - OD[k].x; hs.y += NX[k].y - OD[k].y; hs.z += NX[k].z - OD[k].z; hs.w += NX[k].w - OD[k].w;
+                hs.x += NX[k].x - od.x; hs.y += NX[k].y - od.y; hs.z += NX[k].z - od.z; hs.w += NX[k].w - od.w;
             }
         }
 #pragma unroll
-        for (int k = 0; k < HPF; ++k) { NX[k] = NX2[k]; OD[k] = OD2[k]; }
+        for (int k = 0; k < HPF; ++k) NX[k] = NX2[k];
     }
 }
 
@@ -676,7 +675,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     cudaStream_t st = c->stream;
     const size_t planeStrideR = (size_t)c->maxB * c->H * c->vsRP;
     {
-        dim3 blk(128), grd((c->W + 127) / 128, c->H, 2 * B);
+        dim3 blk(128), grd((c->W + 119) / 120, c->H, 2 * B);      // 4 warps x 30 columns
         KernelTimer kt(c, KID_SGBM_PREFILTER);
         k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->recL, c->plR,
                                               planeStrideR, c->vsRP, c->vsJOFF);
@@ -704,7 +703,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const int TPB = 128;
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
-    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, 0, st>>>(a); }
+    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1) * TPB * 16, st>>>(a); }
     const int nc = c->td_nc;
     auto vdirs = [&](int bottomUp) {
         if (nc > 0) {
@@ -737,6 +736,10 @@ cudaError_t cfg_vsum()
     cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_vsum<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
     if (e != cudaSuccess) return e;
