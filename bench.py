@@ -208,7 +208,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=148,
+                    help="stereo pairs per GPU per step (148 = one per SM: every kernel's grid is a whole number of waves)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

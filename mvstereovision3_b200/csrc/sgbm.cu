@@ -300,7 +300,18 @@ struct AggArgs {
     int storeS;
 };
 
-constexpr int HPF = 2;      // the row scans keep the loads of the next HPF steps in flight (register prefetch)
+// The row scans stream their operands through a per-lane shared-memory ring filled by cp.async (LDGSTS): the
+// loads of the next PFD steps are in flight without holding registers.  Each lane only ever reads back the 16
+// bytes it copied itself, so cp.async.wait_group is the only synchronisation needed.
+constexpr int H1_PFD = 4;
+constexpr int HPF = 2;         // k_sgbm_h2_wta is issue-bound: it keeps a cheap 2-step register prefetch instead
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // K3a: horizontal box sum (VS -> C) fused with the left-to-right path r=(-1,0).  Writes C and S = L.
 template <int G, bool PAD>
@@ -320,44 +331,42 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
     uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
 
-    // ring[s][thread]: the vector that leaves the window at step xi was the entering one bs steps earlier
+    // Stream element t = VS[clamp(t - SW2)], t >= 0.  The window of step xi is t in [xi, xi + bs): it gains
+    // t = xi + bs and loses t = xi.  Ring slot of t is t mod R with R = bs + PFD, so the element fetched at step
+    // xi (t = xi + bs + PFD) lands in the slot of the element that has just left.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* ring = reinterpret_cast<uint4*>(smem_raw) + threadIdx.x;
-    const int bs = 2 * SW2 + 1;
+    const int bs = 2 * SW2 + 1, R = bs + H1_PFD;
+    auto src = [&](int t) { return vs + min(max(t - SW2, 0), W1 - 1) * DP; };
+    for (int t = 0; t < bs; ++t) cp_async16(ring + t * 128, src(t));
+    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < H1_PFD; ++k) { cp_async16(ring + (bs + k) * 128, src(bs + k)); cp_async_commit(); }
+    cp_async_wait<H1_PFD>();
     uint4 hs = make_uint4(0, 0, 0, 0);
-    for (int j = -SW2; j <= SW2; ++j) {
-        const uint4 v = ld128(vs + min(max(j, 0), W1 - 1) * DP);
+    for (int t = 0; t < bs; ++t) {
+        const uint4 v = ring[t * 128];
         hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
-        ring[(j + SW2) * 128] = v;                  // slot of step xi = j + SW2 holds VS[max(xi - SW2, 0)]
     }
     unsigned L[4], mm;
     reset_state<PAD>(L, mm, padLane);
-    uint4 NX[HPF];
-#pragma unroll
-    for (int k = 0; k < HPF; ++k) NX[k] = ld128(vs + min(k + 1 + SW2, W1 - 1) * DP);
-    int slot = 0;
-    for (int x0 = 0; x0 < W1; x0 += HPF) {
-        uint4 NX2[HPF];
-#pragma unroll
-        for (int k = 0; k < HPF; ++k) NX2[k] = ld128(vs + min(x0 + HPF + k + 1 + SW2, W1 - 1) * DP);
-#pragma unroll
-        for (int k = 0; k < HPF; ++k) {
-            const int xi = x0 + k;
-            if (xi < W1) {
-                const uint4 od = ring[slot * 128];
-                ring[slot * 128] = NX[k];
-                if (++slot == bs) slot = 0;
-                sgm_step<G, PAD>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
-                if (active) {
-                    st128(cp + xi * DP, hs);
-                    st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
-                }
-                hs.x += NX[k].x - od.x; hs.y += NX[k].y - od.y; hs.z += NX[k].z - od.z; hs.w += NX[k].w - od.w;
-            }
+    int sOut = 0, sIn = bs;                         // slots of t = xi and t = xi + bs
+    for (int xi = 0; xi < W1; ++xi) {
+        cp_async_wait<H1_PFD - 1>();                // the group issued H1_PFD steps ago (t = xi + bs) has landed
+        const uint4 od = ring[sOut * 128];
+        const uint4 nx = ring[sIn * 128];
+        cp_async16(ring + sOut * 128, src(xi + bs + H1_PFD));
+        cp_async_commit();
+        if (++sOut == R) sOut = 0;
+        if (++sIn == R) sIn = 0;
+        sgm_step<G, PAD>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
+        if (active) {
+            st128(cp + xi * DP, hs);
+            st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
         }
-#pragma unroll
-        for (int k = 0; k < HPF; ++k) NX[k] = NX2[k];
+        hs.x += nx.x - od.x; hs.y += nx.y - od.y; hs.z += nx.z - od.z; hs.w += nx.w - od.w;
     }
+    cp_async_wait<0>();
 }
 
 // K3b: vertical / diagonal paths, one direction per launch (generic fallback when the fused sweep below does
@@ -414,6 +423,16 @@ struct TdArgs {
     unsigned P1P1, P2P2;
 };
 
+// Cluster barrier split by memory semantics: only warps that wrote a neighbour's halo (distributed shared memory)
+// arrive with .release (which costs a fence over their outstanding global stores); all other warps arrive
+// .relaxed -- their shared-memory writes are CTA-local and ordered by the preceding __syncthreads().
+__device__ __forceinline__ void cluster_arrive(bool release)
+{
+    if (release) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 template <int G, bool PAD>
 __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
 {
@@ -447,6 +466,8 @@ __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
     uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
     uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
     uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
+    // warps holding the lane group of the strip's first / last column write the neighbours' halos
+    const bool haloWarp = __any_sync(FULL, (g == 0 && haloL != nullptr) || (g == (M - 1) % NG && haloR != nullptr)) != 0;
     cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
 
     // work item (yi, it): pixel lx = g + it*NG of row yi; its C/S are loaded one item ahead
@@ -519,7 +540,192 @@ __global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
         }
         if (++ymod == M) ymod = 0;
         rowOff += rowStep;
-        cluster.sync();
+        __syncthreads();
+        cluster_arrive(haloWarp);
+        cluster_wait();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16 disparities per lane: lane q of a G2-lane group owns octet q (registers A) and octet q+G2 (registers B) of
+// the pixel (Dp = 16*G2), so that both 128-bit accesses of a warp stay perfectly coalesced.  One recurrence step
+// shares the neighbour shuffles, the min butterfly and all per-pixel bookkeeping between the two octets.
+// ------------------------------------------------------------------------------------------------
+template <int G2, bool PAD>
+__device__ __forceinline__ void sgm_step2(unsigned (&A)[4], unsigned (&B)[4], unsigned& mm, const uint4& Ca, const uint4& Cb,
+                                          unsigned P1P1, unsigned P2P2, int q, bool padA, bool padB)
+{
+    unsigned upA = MVSV_PK_MAX, dnA, upB, dnB = MVSV_PK_MAX;
+    if (G2 > 1) {
+        const int nxt = (q + 1) & (G2 - 1), prv = (q + G2 - 1) & (G2 - 1);
+        const unsigned x = __shfl_sync(FULL, B[0], nxt, G2);     // bottom of octet (q+1)+G2; lane G2-1 gets octet G2
+        const unsigned y = __shfl_sync(FULL, A[0], nxt, G2);     // bottom of octet q+1
+        const unsigned u = __shfl_sync(FULL, A[3], prv, G2);     // top of octet q-1; lane 0 gets octet G2-1
+        const unsigned w = __shfl_sync(FULL, B[3], prv, G2);     // top of octet q-1+G2
+        dnA = (q == G2 - 1) ? x : y;
+        if (q != G2 - 1) dnB = x;
+        if (q != 0) upA = u;
+        upB = (q == 0) ? u : w;
+    } else {
+        dnA = B[0]; upB = A[3];
+    }
+    const unsigned mP2 = __vadd2(mm, P2P2);
+    const unsigned XA0 = __byte_perm(upA, A[0], 0x5432), XA1 = __byte_perm(A[0], A[1], 0x5432);
+    const unsigned XA2 = __byte_perm(A[1], A[2], 0x5432), XA3 = __byte_perm(A[2], A[3], 0x5432);
+    const unsigned XA4 = __byte_perm(A[3], dnA, 0x5432);
+    const unsigned XB0 = __byte_perm(upB, B[0], 0x5432), XB1 = __byte_perm(B[0], B[1], 0x5432);
+    const unsigned XB2 = __byte_perm(B[1], B[2], 0x5432), XB3 = __byte_perm(B[2], B[3], 0x5432);
+    const unsigned XB4 = __byte_perm(B[3], dnB, 0x5432);
+    unsigned a0 = __vminu2(__viaddmin_u16x2(__vminu2(XA0, XA1), P1P1, A[0]), mP2) + Ca.x - mm;
+    unsigned a1 = __vminu2(__viaddmin_u16x2(__vminu2(XA1, XA2), P1P1, A[1]), mP2) + Ca.y - mm;
+    unsigned a2 = __vminu2(__viaddmin_u16x2(__vminu2(XA2, XA3), P1P1, A[2]), mP2) + Ca.z - mm;
+    unsigned a3 = __vminu2(__viaddmin_u16x2(__vminu2(XA3, XA4), P1P1, A[3]), mP2) + Ca.w - mm;
+    unsigned b0 = __vminu2(__viaddmin_u16x2(__vminu2(XB0, XB1), P1P1, B[0]), mP2) + Cb.x - mm;
+    unsigned b1 = __vminu2(__viaddmin_u16x2(__vminu2(XB1, XB2), P1P1, B[1]), mP2) + Cb.y - mm;
+    unsigned b2 = __vminu2(__viaddmin_u16x2(__vminu2(XB2, XB3), P1P1, B[2]), mP2) + Cb.z - mm;
+    unsigned b3 = __vminu2(__viaddmin_u16x2(__vminu2(XB3, XB4), P1P1, B[3]), mP2) + Cb.w - mm;
+    if (PAD && padA) { a0 = a1 = a2 = a3 = MVSV_PK_MAX; }
+    if (PAD && padB) { b0 = b1 = b2 = b3 = MVSV_PK_MAX; }
+    unsigned m = __vimin3_u16x2(__vimin3_u16x2(a0, a1, a2), __vimin3_u16x2(a3, b0, b1), __vimin3_u16x2(b2, b3, b3));
+#pragma unroll
+    for (int o = G2 / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G2));
+    mm = __vminu2(m, __byte_perm(m, 0, 0x1032));
+    A[0] = a0; A[1] = a1; A[2] = a2; A[3] = a3;
+    B[0] = b0; B[1] = b1; B[2] = b2; B[3] = b3;
+}
+
+template <bool PAD>
+__device__ __forceinline__ void reset_state2(unsigned (&A)[4], unsigned (&B)[4], unsigned& mm, bool padA, bool padB)
+{
+    const unsigned va = (PAD && padA) ? MVSV_PK_MAX : 0u, vb = (PAD && padB) ? MVSV_PK_MAX : 0u;
+    A[0] = A[1] = A[2] = A[3] = va;
+    B[0] = B[1] = B[2] = B[3] = vb;
+    mm = 0u;
+}
+
+// K3b'' -- the fused previous-row sweep (see k_sgbm_td above for the scheme) with 16 disparities per lane.
+constexpr int TD2_THREADS = 512;      // launch bound; the launcher picks 256 or 512 threads per CTA
+
+template <int G2, bool PAD>
+__global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: L[3][Mmax][Dp] u16 | halo[2 parity][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[2][2] u32
+    constexpr int Dp = 16 * G2;                     // == a.Dp
+    constexpr int OB = 8 * G2;                      // element offset of the lane's second octet
+    uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* halo = Lb + (size_t)3 * a.Mmax * Dp;
+    unsigned* mb = reinterpret_cast<unsigned*>(halo + 4 * Dp);
+    unsigned* halom = mb + 3 * a.Mmax;
+
+    const int r = (int)cluster.block_rank();
+    const int f = blockIdx.y;
+    const int x0 = (int)(((long long)a.W1 * r) / a.NC), x1 = (int)(((long long)a.W1 * (r + 1)) / a.NC);
+    const int M = x1 - x0;
+    const int NG = blockDim.x / G2;
+    const int g = threadIdx.x / G2, q = threadIdx.x % G2;
+    const bool padA = q * 8 >= a.D, padB = (q + G2) * 8 >= a.D;
+    uint16_t* haloR = (r + 1 < a.NC) ? cluster.map_shared_rank(halo, r + 1) : nullptr;   // CTA owning columns x1..
+    uint16_t* haloL = (r > 0) ? cluster.map_shared_rank(halo, r - 1) : nullptr;
+    unsigned* halomR = (r + 1 < a.NC) ? cluster.map_shared_rank(halom, r + 1) : nullptr;
+    unsigned* halomL = (r > 0) ? cluster.map_shared_rank(halom, r - 1) : nullptr;
+    const int iters = (M + NG - 1) / NG;
+    const int Mmax = a.Mmax, W1 = a.W1;
+    const int rowElems = W1 * Dp;
+    const uint16_t* __restrict__ cbase = a.C + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
+    uint16_t* __restrict__ sbase = a.S + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
+    const int rowStep = a.bottomUp ? -rowElems : rowElems;
+    uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
+    uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
+    uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
+    const bool haloWarp = __any_sync(FULL, (g == 0 && haloL != nullptr) || (g == (M - 1) % NG && haloR != nullptr)) != 0;
+    cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
+
+    const int lxFirst = min(g, M - 1);
+    uint4 CnA = ld128(cbase + lxFirst * Dp), CnB = ld128(cbase + lxFirst * Dp + OB);
+    uint4 SnA = ld128(sbase + lxFirst * Dp), SnB = ld128(sbase + lxFirst * Dp + OB);
+    int ymod = 0, rowOff = 0;
+    for (int yi = 0; yi < a.H; ++yi) {
+        const int par = yi & 1;
+        const bool firstRow = yi == 0;
+        for (int it = 0; it < iters; ++it) {
+            int lx = g + it * NG;
+            const bool active = lx < M;
+            if (!active) lx = M - 1;
+            const int x = x0 + lx;
+            const int off = rowOff + lx * Dp;
+            const uint4 CcA = CnA, CcB = CnB;
+            uint4 ScA = SnA, ScB = SnB;
+            {
+                const bool lastIt = it + 1 == iters;
+                const int nlx = min(lastIt ? g : g + (it + 1) * NG, M - 1);
+                const int noff = (lastIt ? rowOff + rowStep : rowOff) + nlx * Dp;
+                if (!(lastIt && yi + 1 == a.H)) {
+                    CnA = ld128(cbase + noff); CnB = ld128(cbase + noff + OB);
+                    SnA = ld128(sbase + noff); SnB = ld128(sbase + noff + OB);
+                }
+            }
+            unsigned A[4], B[4], mm;
+            // ---- vertical path, slot lx
+            {
+                uint16_t* sl = L1b + lx * Dp;
+                ld_state(A, sl); ld_state(B, sl + OB); mm = mb[Mmax + lx];
+                if (firstRow) reset_state2<PAD>(A, B, mm, padA, padB);
+                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
+                if (active) {
+                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    if (q == 0) mb[Mmax + lx] = mm;
+                }
+                sat_acc(ScA, A); sat_acc(ScB, B);
+            }
+            // ---- diagonal with predecessor (x-1, previous row): slot (lx - yi) mod M, halo from the left CTA
+            {
+                int s1 = lx - ymod; if (s1 < 0) s1 += M;
+                uint16_t* sl = L0b + s1 * Dp;
+                const bool fromHalo = lx == 0;
+                const uint16_t* src = fromHalo ? halo + (par * 2 + 0) * Dp + q * 8 : sl;
+                ld_state(A, src); ld_state(B, src + OB); mm = fromHalo ? halom[par * 2 + 0] : mb[s1];
+                if (firstRow || x == 0) reset_state2<PAD>(A, B, mm, padA, padB);
+                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
+                if (active) {
+                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    if (q == 0) mb[s1] = mm;
+                    if (lx == M - 1 && haloR) {
+                        uint16_t* h = haloR + ((par ^ 1) * 2 + 0) * Dp + q * 8;
+                        st128(h, make_uint4(A[0], A[1], A[2], A[3])); st128(h + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                        if (q == 0) halomR[(par ^ 1) * 2 + 0] = mm;
+                    }
+                }
+                sat_acc(ScA, A); sat_acc(ScB, B);
+            }
+            // ---- diagonal with predecessor (x+1, previous row): slot (lx + yi) mod M, halo from the right CTA
+            {
+                int s3 = lx + ymod; if (s3 >= M) s3 -= M;
+                uint16_t* sl = L2b + s3 * Dp;
+                const bool fromHalo = lx == M - 1;
+                const uint16_t* src = fromHalo ? halo + (par * 2 + 1) * Dp + q * 8 : sl;
+                ld_state(A, src); ld_state(B, src + OB); mm = fromHalo ? halom[par * 2 + 1] : mb[2 * Mmax + s3];
+                if (firstRow || x == W1 - 1) reset_state2<PAD>(A, B, mm, padA, padB);
+                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
+                if (active) {
+                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    if (q == 0) mb[2 * Mmax + s3] = mm;
+                    if (lx == 0 && haloL) {
+                        uint16_t* h = haloL + ((par ^ 1) * 2 + 1) * Dp + q * 8;
+                        st128(h, make_uint4(A[0], A[1], A[2], A[3])); st128(h + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                        if (q == 0) halomL[(par ^ 1) * 2 + 1] = mm;
+                    }
+                }
+                sat_acc(ScA, A); sat_acc(ScB, B);
+            }
+            if (active) { st128(sbase + off, ScA); st128(sbase + off + OB, ScB); }
+        }
+        if (++ymod == M) ymod = 0;
+        rowOff += rowStep;
+        __syncthreads();
+        cluster_arrive(haloWarp);
+        cluster_wait();
     }
 }
 
@@ -663,6 +869,9 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
+// threads per CTA of the 16-disparity sweep: 512 when the strip gives every lane group >= 2 pixels per row
+inline int td2_threads(int Mmax, int G2) { return (Mmax * G2 >= 1024) ? 512 : 256; }
+
 inline size_t td_smem_bytes(int Mmax, int Dp)
 {
     return (size_t)3 * Mmax * Dp * 2 + (size_t)4 * Dp * 2 + (size_t)3 * Mmax * 4 + 4 * 4 + 16;
@@ -703,7 +912,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const int TPB = 128;
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
-    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1) * TPB * 16, st>>>(a); }
+    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16, st>>>(a); }
     const int nc = c->td_nc;
     auto vdirs = [&](int bottomUp) {
         if (nc > 0) {
@@ -718,7 +927,12 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
             at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             KernelTimer kt(c, KID_SGBM_TD);
-            cudaLaunchKernelEx(&cfg, k_sgbm_td<G, PAD>, t);
+            if constexpr (G >= 2) {
+                cfg.blockDim = dim3(td2_threads(t.Mmax, G / 2), 1, 1);
+                cudaLaunchKernelEx(&cfg, k_sgbm_td2<G / 2, PAD>, t);
+            } else {
+                cudaLaunchKernelEx(&cfg, k_sgbm_td<G, PAD>, t);
+            }
         } else {
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
@@ -747,20 +961,35 @@ cudaError_t cfg_vsum()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    if constexpr (G >= 2) {
+        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 template <int G>
-int td_max_clusters(int nc, size_t smem)
+int td_max_clusters(int nc, size_t smem, int Mmax)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nc, 1, 1); cfg.blockDim = dim3(TD_THREADS, 1, 1); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3(nc, 1, 1); cfg.blockDim = dim3(G >= 2 ? td2_threads(Mmax, G / 2) : TD_THREADS, 1, 1); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G, false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaError_t e;
+    if constexpr (G >= 2) e = cudaOccupancyMaxActiveClusters(&n, k_sgbm_td2<G / 2, false>, &cfg);
+    else e = cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G, false>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -779,7 +1008,7 @@ cudaError_t sgbm_configure_kernels()
 }
 
 // Cluster size for the fused previous-row sweep: the smallest power of two whose column strip fits in shared
-// memory, raised to 4 when the frame is wide enough (more CTAs per frame = more SMs busy at small batches).
+// memory (clusters of 2 pack the 148 SMs exactly; clusters of 4 strand 16 of them, measured).
 // 0 = does not fit (or clusters unavailable): fall back to the three independent k_sgbm_vdir passes.
 int sgbm_choose_td_cluster(const mvsv_ctx* c)
 {
@@ -793,15 +1022,14 @@ int sgbm_choose_td_cluster(const mvsv_ctx* c)
         const int Mmax = (n.W1 + nc - 1) / nc;
         const size_t smem = td_smem_bytes(Mmax, n.Dp);
         if (smem > (size_t)TD_SMEM_LIMIT) continue;
-        if (!forced && nc < 4 && n.W1 >= 4 * 32) continue;
         int ok = 0;
         switch (n.G) {
-            case 1: ok = td_max_clusters<1>(nc, smem); break;
-            case 2: ok = td_max_clusters<2>(nc, smem); break;
-            case 4: ok = td_max_clusters<4>(nc, smem); break;
-            case 8: ok = td_max_clusters<8>(nc, smem); break;
-            case 16: ok = td_max_clusters<16>(nc, smem); break;
-            default: ok = td_max_clusters<32>(nc, smem); break;
+            case 1: ok = td_max_clusters<1>(nc, smem, Mmax); break;
+            case 2: ok = td_max_clusters<2>(nc, smem, Mmax); break;
+            case 4: ok = td_max_clusters<4>(nc, smem, Mmax); break;
+            case 8: ok = td_max_clusters<8>(nc, smem, Mmax); break;
+            case 16: ok = td_max_clusters<16>(nc, smem, Mmax); break;
+            default: ok = td_max_clusters<32>(nc, smem, Mmax); break;
         }
         if (ok > 0) return nc;
     }
