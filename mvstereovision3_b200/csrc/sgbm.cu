@@ -99,11 +99,41 @@ __device__ __forceinline__ unsigned bt_pair(unsigned v, unsigned v0, unsigned nv
     return __vmins2(c0, c1);
 }
 
-template <int G, bool R8>
-__global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
+// cp.async (LDGSTS) helpers: asynchronous global -> shared copies, completion tracked per thread in groups
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
-    constexpr int PX = VS_THREADS / G;
-    constexpr int MAXIT = (G == 32 || G == 1) ? 2 : 1;  // staging items (6 arrays x NV vectors, NV <= 64) per thread
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int VS_RD = 4;       // raw-ring depth of the cost kernel's producer (rows in flight + 1)
+
+// geometry fixed by G: entries a CTA can touch, 8-entry vectors per channel (power of two), producer warps
+template <int G> struct VsGeom {
+    static constexpr int PX = VS_THREADS / G;
+    static constexpr int NE = PX - 1 + 8 * G;
+    static constexpr int NV = (NE + 2 <= 16) ? 2 : (NE + 2 <= 32) ? 4 : (NE + 2 <= 64) ? 8 : (NE + 2 <= 128) ? 16 : (NE + 2 <= 256) ? 32 : 64;
+    static constexpr int ITEMS = 6 * NV;                       // (channel, vector) staging items per row
+    static constexpr int NPW = (ITEMS + 95) / 96;              // producer warps: <= 3 items per producer lane
+    static constexpr int NPT = 32 * NPW;                       // producer threads
+    static constexpr int IPL = (ITEMS + NPT - 1) / NPT;        // items per producer lane
+    static constexpr int RPL = (PX + NPT - 1) / NPT;           // left records per producer lane
+    static constexpr int THREADS = VS_THREADS + NPT;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int G, bool R8>
+__global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
+{
+    using GE = VsGeom<G>;
+    constexpr int PX = GE::PX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: sR[2 buf][6][8][LEN] u16 | sL[2 buf][PX][12] u32 | ring[bs][VS_THREADS] (uint2 if the pixel cost
     // fits a byte -- 2*ftzero+63 <= 255 -- else uint4)
@@ -112,90 +142,118 @@ __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
     unsigned char* ring = reinterpret_cast<unsigned char*>(sL + 2 * PX * 12);
 
     const int tid = threadIdx.x;
-    const int p = tid / G, q = tid % G;
     const int f = blockIdx.y;
     const int xa = blockIdx.x * PX;
+    const int bs = 2 * a.SH2 + 1;
+    const int steps = a.H + 2 * a.SH2;
+    const size_t rowsR = (size_t)f * a.H;
+    // named barriers: 1 + buf = "stage buf is full", 3 + buf = "stage buf is free again"
+    constexpr int NTH = GE::THREADS;
+
+    if (tid >= VS_THREADS) {
+        // ===================== producer warps: stage row t while the compute warps consume row t-1 ===============
+        // Global loads run VS_RD-1 rows ahead through cp.async into a private raw ring (every lane reads back only
+        // what it copied), so the producer's critical path is LDS -> funnel shifts -> STS.
+        const int pt = tid - VS_THREADS;
+        const int xr_max = xa + PX - 1 + a.minX1 - a.minD;       // entry e <-> right column xr_max - e
+        const int j0 = a.JOFF + a.W - 1 - xr_max;                // reversed-plane index of entry 0 (multiple of 8)
+        uint4* rawPQ = reinterpret_cast<uint4*>(ring + (size_t)bs * VS_THREADS * (R8 ? 8 : 16));   // [VS_RD][IPL][2][NPT]
+        uint2* rawL = reinterpret_cast<uint2*>(rawPQ + VS_RD * GE::IPL * 2 * GE::NPT);             // [VS_RD][RPL][NPT]
+        size_t srcOff[GE::IPL]; int dstOff[GE::IPL]; bool itemOn[GE::IPL];
+#pragma unroll
+        for (int k = 0; k < GE::IPL; ++k) {
+            const int item = pt + k * GE::NPT;
+            itemOn[k] = item < GE::ITEMS;
+            const int arr = itemOn[k] ? item / GE::NV : 0, m = itemOn[k] ? item % GE::NV : 0;
+            srcOff[k] = (size_t)arr * a.planeStrideR + rowsR * a.RP + j0 + 8 * m;
+            dstOff[k] = arr * 8 * a.LEN + 8 * m;
+        }
+        auto issue_loads = [&](int t) {
+            if (t < steps) {
+                const int y = min(max(t - a.SH2, 0), a.H - 1);
+                const int rs = t % VS_RD;
+#pragma unroll
+                for (int k = 0; k < GE::IPL; ++k) {
+                    if (itemOn[k]) {
+                        const uint16_t* src = a.plR + srcOff[k] + (size_t)y * a.RP;
+                        uint4* d = rawPQ + ((rs * GE::IPL + k) * 2) * GE::NPT + pt;
+                        cp_async16(d, src - 8);
+                        cp_async16(d + GE::NPT, src);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < GE::RPL; ++k) {
+                    const int px = pt + k * GE::NPT;
+                    if (px < PX && xa + px < a.W1)
+                        cp_async8(rawL + (rs * GE::RPL + k) * GE::NPT + pt, a.recL + (rowsR + y) * a.W + xa + px + a.minX1);
+                }
+            }
+            cp_async_commit();
+        };
+        auto store_stage = [&](int buf, int t) {
+            const int rs = t % VS_RD;
+#pragma unroll
+            for (int k = 0; k < GE::IPL; ++k) {
+                if (itemOn[k]) {
+                    uint16_t* dst = sR + (size_t)buf * 6 * 8 * a.LEN + dstOff[k];
+                    const uint4* d = rawPQ + ((rs * GE::IPL + k) * 2) * GE::NPT + pt;
+                    const uint4 p4 = d[0], q4 = d[GE::NPT];
+                    const unsigned f0 = __funnelshift_r(p4.x, p4.y, 16), f1 = __funnelshift_r(p4.y, p4.z, 16);
+                    const unsigned f2 = __funnelshift_r(p4.z, p4.w, 16), f3 = __funnelshift_r(p4.w, q4.x, 16);
+                    const unsigned f4 = __funnelshift_r(q4.x, q4.y, 16), f5 = __funnelshift_r(q4.y, q4.z, 16);
+                    const unsigned f6 = __funnelshift_r(q4.z, q4.w, 16);
+                    // copy s holds entry e at position e+s: positions [8m, 8m+8) of copy s = entries [8m-s, 8m-s+8)
+                    st128(dst + 0 * a.LEN, q4);
+                    st128(dst + 1 * a.LEN, make_uint4(f3, f4, f5, f6));
+                    st128(dst + 2 * a.LEN, make_uint4(p4.w, q4.x, q4.y, q4.z));
+                    st128(dst + 3 * a.LEN, make_uint4(f2, f3, f4, f5));
+                    st128(dst + 4 * a.LEN, make_uint4(p4.z, p4.w, q4.x, q4.y));
+                    st128(dst + 5 * a.LEN, make_uint4(f1, f2, f3, f4));
+                    st128(dst + 6 * a.LEN, make_uint4(p4.y, p4.z, p4.w, q4.x));
+                    st128(dst + 7 * a.LEN, make_uint4(f0, f1, f2, f3));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < GE::RPL; ++k) {
+                const int px = pt + k * GE::NPT;
+                if (px < PX) {
+                    // words: 0 uu_s 1 nuu_s 2 uu1_s 3 uu0_s 4 kk_s 5 uu_r 6 nuu_r 7 uu1_r 8 uu0_r 9 kk_r
+                    const uint2 lr = (xa + px < a.W1) ? rawL[(rs * GE::RPL + k) * GE::NPT + pt] : make_uint2(0, 0);
+                    const int us = lr.x & 0xff, los = (lr.x >> 8) & 0xff, his = (lr.x >> 16) & 0xff, ur = lr.x >> 24;
+                    const int lor = lr.y & 0xff, hir = (lr.y >> 8) & 0xff;
+                    unsigned* d = sL + (buf * PX + px) * 12;
+                    st128(d, make_uint4(pk16(us), pk16(-us), pk16(his), pk16(los)));
+                    st128(d + 4, make_uint4(pk16(his - los), pk16(ur), pk16(-ur), pk16(hir)));
+                    st128(d + 8, make_uint4(pk16(lor), pk16(hir - lor), 0u, 0u));
+                }
+            }
+        };
+#pragma unroll
+        for (int t0 = 0; t0 < VS_RD - 1; ++t0) issue_loads(t0);
+        for (int t = 0; t < steps; ++t) {
+            const int buf = t & 1;
+            issue_loads(t + VS_RD - 1);                        // into the raw slot consumed at step t-1
+            cp_async_wait<VS_RD - 1>();                        // row t has landed
+            if (t >= 2) named_bar_sync(3 + buf, NTH);          // compute warps are done with row t-2 (same buffer)
+            store_stage(buf, t);
+            named_bar_arrive(1 + buf, NTH);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+
+    // ===================== compute warps ==========================================================================
+    const int p = tid / G, q = tid % G;
     const int xi = xa + p;
     const bool live = (xi < a.W1) && (q * 8 < a.D);
-    const int bs = 2 * a.SH2 + 1;
-    const int xr_max = xa + PX - 1 + a.minX1 - a.minD;       // entry e <-> right column xr_max - e
-    const int j0 = a.JOFF + a.W - 1 - xr_max;                // reversed-plane index of entry 0 (multiple of 8)
     const int e0 = (PX - 1 - p) + 8 * q;
     const int sh = (-e0) & 7;
     const int rbase = sh * a.LEN + e0 + sh;                   // + (buf*6 + arr)*8*LEN
-    const int nitems = 6 * a.NV;
-    const int steps = a.H + 2 * a.SH2;
-    const size_t rowsR = (size_t)f * a.H;
-
-    // staging registers: for item (arr, m) the aligned vectors of entries [8m-8, 8m) and [8m, 8m+8)
-    uint4 P[MAXIT], Q[MAXIT];
-    uint2 lrec = make_uint2(0, 0);
-    size_t srcOff[MAXIT]; int dstOff[MAXIT]; bool itemOn[MAXIT];
-#pragma unroll
-    for (int k = 0; k < MAXIT; ++k) {
-        const int item = tid + k * VS_THREADS;
-        itemOn[k] = item < nitems;
-        const int arr = itemOn[k] ? item / a.NV : 0, m = itemOn[k] ? item - arr * a.NV : 0;
-        srcOff[k] = (size_t)arr * a.planeStrideR + rowsR * a.RP + j0 + 8 * m;
-        dstOff[k] = arr * 8 * a.LEN + 8 * m;
-    }
-    auto issue_loads = [&](int t) {
-        const int y = min(max(t - a.SH2, 0), a.H - 1);
-#pragma unroll
-        for (int k = 0; k < MAXIT; ++k) {
-            if (itemOn[k]) {
-                const uint16_t* src = a.plR + srcOff[k] + (size_t)y * a.RP;
-                P[k] = ld128(src - 8);
-                Q[k] = ld128(src);
-            }
-        }
-        if (tid < PX) lrec = (xa + tid < a.W1) ? a.recL[(rowsR + y) * a.W + xa + tid + a.minX1] : make_uint2(0, 0);
-    };
-    auto store_stage = [&](int buf) {
-#pragma unroll
-        for (int k = 0; k < MAXIT; ++k) {
-            if (itemOn[k]) {
-                uint16_t* dst = sR + (size_t)buf * 6 * 8 * a.LEN + dstOff[k];
-                const uint4 p4 = P[k], q4 = Q[k];
-                const unsigned f0 = __funnelshift_r(p4.x, p4.y, 16), f1 = __funnelshift_r(p4.y, p4.z, 16);
-                const unsigned f2 = __funnelshift_r(p4.z, p4.w, 16), f3 = __funnelshift_r(p4.w, q4.x, 16);
-                const unsigned f4 = __funnelshift_r(q4.x, q4.y, 16), f5 = __funnelshift_r(q4.y, q4.z, 16);
-                const unsigned f6 = __funnelshift_r(q4.z, q4.w, 16);
-                // copy s holds entry e at position e+s: positions [8m, 8m+8) of copy s = entries [8m-s, 8m-s+8)
-                st128(dst + 0 * a.LEN, q4);
-                st128(dst + 1 * a.LEN, make_uint4(f3, f4, f5, f6));
-                st128(dst + 2 * a.LEN, make_uint4(p4.w, q4.x, q4.y, q4.z));
-                st128(dst + 3 * a.LEN, make_uint4(f2, f3, f4, f5));
-                st128(dst + 4 * a.LEN, make_uint4(p4.z, p4.w, q4.x, q4.y));
-                st128(dst + 5 * a.LEN, make_uint4(f1, f2, f3, f4));
-                st128(dst + 6 * a.LEN, make_uint4(p4.y, p4.z, p4.w, q4.x));
-                st128(dst + 7 * a.LEN, make_uint4(f0, f1, f2, f3));
-            }
-        }
-        if (tid < PX) {
-            // words: 0 uu_s 1 nuu_s 2 uu1_s 3 uu0_s 4 kk_s 5 uu_r 6 nuu_r 7 uu1_r 8 uu0_r 9 kk_r
-            const int us = lrec.x & 0xff, los = (lrec.x >> 8) & 0xff, his = (lrec.x >> 16) & 0xff, ur = lrec.x >> 24;
-            const int lor = lrec.y & 0xff, hir = (lrec.y >> 8) & 0xff;
-            unsigned* d = sL + (buf * PX + tid) * 12;
-            st128(d, make_uint4(pk16(us), pk16(-us), pk16(his), pk16(los)));
-            st128(d + 4, make_uint4(pk16(his - los), pk16(ur), pk16(-ur), pk16(hir)));
-            st128(d + 8, make_uint4(pk16(lor), pk16(hir - lor), 0u, 0u));
-        }
-    };
-
-    issue_loads(0);
-    store_stage(0);
-    if (steps > 1) issue_loads(1);
-    __syncthreads();
-
     uint4 acc = make_uint4(0, 0, 0, 0);
     int slot = 0;
     for (int t = 0; t < steps; ++t) {
         const int buf = t & 1;
-        if (t + 1 < steps) {
-            store_stage(buf ^ 1);                 // row t+1 (loaded during step t-1)
-            if (t + 2 < steps) issue_loads(t + 2);
-        }
+        named_bar_sync(1 + buf, NTH);
         if (live) {
             const uint16_t* rb = sR + (size_t)buf * 6 * 8 * a.LEN + rbase;
             const uint4 A0 = ld128(rb + 0 * 8 * a.LEN), A1 = ld128(rb + 1 * 8 * a.LEN), A2 = ld128(rb + 2 * 8 * a.LEN);
@@ -231,8 +289,10 @@ __global__ void __launch_bounds__(VS_THREADS) k_sgbm_vsum(VsArgs a)
                 st128(a.VS + (((size_t)f * a.H + yo) * a.W1 + xi) * a.Dp + q * 8, acc);
             }
         }
+        // barrier instructions need a converged warp (`live` differs between lanes in edge CTAs / padded lanes)
+        __syncwarp();
+        if (t + 2 < steps) named_bar_arrive(3 + buf, NTH);       // stage buffer consumed: hand it back
         if (++slot == bs) slot = 0;
-        __syncthreads();
     }
 }
 
@@ -305,13 +365,7 @@ struct AggArgs {
 // bytes it copied itself, so cp.async.wait_group is the only synchronisation needed.
 constexpr int H1_PFD = 4;
 constexpr int HPF = 2;         // k_sgbm_h2_wta is issue-bound: it keeps a cheap 2-step register prefetch instead
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 
 // K3a: horizontal box sum (VS -> C) fused with the left-to-right path r=(-1,0).  Writes C and S = L.
 template <int G, bool PAD>
@@ -896,12 +950,14 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         a.VS = c->VS; a.W = c->W; a.H = c->H; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.minD = n.minD; a.minX1 = n.minX1;
         a.SH2 = n.SH2; a.NV = c->vsNV; a.LEN = 8 * c->vsNV + 8; a.RP = c->vsRP; a.JOFF = c->vsJOFF;
         const bool r8 = 2 * n.ftzero + 63 <= 255;
+        using GE = VsGeom<G>;
         const size_t smem = (size_t)2 * 6 * 8 * a.LEN * 2 + (size_t)2 * PX * 12 * 4 +
-                            (size_t)(2 * n.SH2 + 1) * VS_THREADS * (r8 ? 8 : 16);
+                            (size_t)(2 * n.SH2 + 1) * VS_THREADS * (r8 ? 8 : 16) +
+                            (size_t)VS_RD * GE::IPL * 2 * GE::NPT * 16 + (size_t)VS_RD * GE::RPL * GE::NPT * 8;
         dim3 grd((n.W1 + PX - 1) / PX, B);
         KernelTimer kt(c, KID_SGBM_VSUM);
-        if (r8) k_sgbm_vsum<G, true><<<grd, VS_THREADS, smem, st>>>(a);
-        else k_sgbm_vsum<G, false><<<grd, VS_THREADS, smem, st>>>(a);
+        if (r8) k_sgbm_vsum<G, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+        else k_sgbm_vsum<G, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
