@@ -288,19 +288,44 @@ def main():
     fps = frames_total / (ms_max * 1e-3)
 
     # ---- end to end through the host-facing call -------------------------------------------------
-    for _ in range(2):
-        step_e2e()
+    # Two engines (two streams, two sets of pinned host buffers) are software-pipelined: while one engine's
+    # result is copied back and awaited, the other engine's H2D copies and kernels run.  Every step still does
+    # its own host->device copy of 2*B*H*W bytes and device->host copy of the B disparity maps.
+    eng2 = api.Engine(W, H, max_batch=B, device=local_rank)
+    eng2.set_sgbm_params(**p)
+    hl2, hr2, hd2 = api.pinned((B, H, W), np.uint8), api.pinned((B, H, W), np.uint8), api.pinned((B, H, W), np.int16)
+    hl2.array[:] = hl.array
+    hr2.array[:] = hr.array
+    lanes = [(eng, hl, hr, hd), (eng2, hl2, hr2, hd2)]
+
+    def submit(k):
+        e, a_, b_, _ = lanes[k & 1]
+        e.compute(a_.array, b_.array, stages)           # async: pinned H2D + kernels on the engine's stream
+
+    def collect(k):
+        e, _, _, d_ = lanes[k & 1]
+        e.download(B, out={"disp": d_.array})           # D2H on the same stream, then stream sync
+
+    def e2e_loop(n):
+        submit(0)
+        for k in range(1, n):
+            submit(k)
+            collect(k - 1)
+        collect(n - 1)
+
+    e2e_loop(4)
+    eng2.sync()
     fence()
-    eng.timer_start()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    ms_e2e_dev = eng.timer_stop()
-    ms_e2e = max(ms_e2e_dev, (time.perf_counter() - t0) * 1e3)      # download() syncs: host clock >= device clock
+    e2e_loop(args.steps)
+    eng2.sync()
+    eng.sync()
+    ms_e2e = (time.perf_counter() - t0) * 1e3          # host clock between two device synchronisations
     fence()
     ms_e2e_max, frames_e2e = shard.reduce_max_and_sum(dist, dev, ms_e2e, B * args.steps)
     fps_e2e = frames_e2e / (ms_e2e_max * 1e-3)
     gpu_disp = hd.array[:uniq].copy()
+    assert np.array_equal(hd.array, hd2.array), "the two pipelined engines disagree"
 
     if rank != 0:
         if dist is not None:
@@ -360,6 +385,7 @@ def main():
                              % (B, 3 * 2 * cells_per_frame * B / 1e9)},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * H * W,
                     "d2h_bytes_per_step": 2 * B * H * W, "ms_per_step": ms_e2e_max / args.steps,
+                    "pipeline": "2 engines / 2 streams, pinned host buffers; host clock between device syncs",
                     "gdisp_evals_per_s": W * H * p["numDisp"] * fps_e2e / 1e9},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_path": roofline_path,
             "kernels": kern, "cpu_baseline": cpu, "parity": parity}
