@@ -668,6 +668,12 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
     // layout: L[3][Mmax][Dp] u16 | halo[2 parity][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[2][2] u32
     constexpr int Dp = 16 * G2;                     // == a.Dp
     constexpr int OB = 8 * G2;                      // element offset of the lane's second octet
+    // Bank-conflict swizzle of the state slots: a quarter-warp phase (8 lanes) covers 8/G2 pixels that each touch
+    // one half (16*G2 bytes) of their slot; slots of 32*G2 bytes repeat every 4/G2 pixels in the 128-byte bank
+    // space, so the two halves are exchanged for every other group of 4/G2 slots.  Keyed on the slot index, hence
+    // the same for the writer and the reader of a slot.
+    constexpr int SWS = (G2 == 4) ? 0 : (G2 == 2) ? 1 : (G2 == 1) ? 2 : -1;
+    auto offA = [&](int slot) { return (SWS >= 0 && ((slot >> (SWS < 0 ? 0 : SWS)) & 1)) ? OB : 0; };
     uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* halo = Lb + (size_t)3 * a.Mmax * Dp;
     unsigned* mb = reinterpret_cast<unsigned*>(halo + 4 * Dp);
@@ -694,7 +700,14 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
     uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
     uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
     const bool haloWarp = __any_sync(FULL, (g == 0 && haloL != nullptr) || (g == (M - 1) % NG && haloR != nullptr)) != 0;
-    cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
+    if (!PAD) {
+        // "No predecessor" is the state (L = 0, m = 0).  Zero every slot once (first row) and both halos (the
+        // frame's left / right border never receives a neighbour's write), so the row loop needs no reset tests.
+        const int nwords = (3 * Mmax * Dp + 4 * Dp) / 2 + 3 * Mmax + 4;     // L, halo (u16 pairs), m, halom
+        unsigned* wz = reinterpret_cast<unsigned*>(smem_raw);
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) wz[i] = 0u;
+    }
+    cluster.sync();     // every CTA of the cluster is resident (and initialised) before any remote access
 
     const int lxFirst = min(g, M - 1);
     uint4 CnA = ld128(cbase + lxFirst * Dp), CnB = ld128(cbase + lxFirst * Dp + OB);
@@ -724,11 +737,12 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
             // ---- vertical path, slot lx
             {
                 uint16_t* sl = L1b + lx * Dp;
-                ld_state(A, sl); ld_state(B, sl + OB); mm = mb[Mmax + lx];
-                if (firstRow) reset_state2<PAD>(A, B, mm, padA, padB);
+                const int oa = offA(lx), ob = OB - oa;
+                ld_state(A, sl + oa); ld_state(B, sl + ob); mm = mb[Mmax + lx];
+                if (PAD && firstRow) reset_state2<PAD>(A, B, mm, padA, padB);
                 sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
                 if (active) {
-                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
                     if (q == 0) mb[Mmax + lx] = mm;
                 }
                 sat_acc(ScA, A); sat_acc(ScB, B);
@@ -738,12 +752,13 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
                 int s1 = lx - ymod; if (s1 < 0) s1 += M;
                 uint16_t* sl = L0b + s1 * Dp;
                 const bool fromHalo = lx == 0;
+                const int oa = offA(s1), ob = OB - oa;
                 const uint16_t* src = fromHalo ? halo + (par * 2 + 0) * Dp + q * 8 : sl;
-                ld_state(A, src); ld_state(B, src + OB); mm = fromHalo ? halom[par * 2 + 0] : mb[s1];
-                if (firstRow || x == 0) reset_state2<PAD>(A, B, mm, padA, padB);
+                ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 0] : mb[s1];
+                if (PAD && (firstRow || x == 0)) reset_state2<PAD>(A, B, mm, padA, padB);
                 sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
                 if (active) {
-                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
                     if (q == 0) mb[s1] = mm;
                     if (lx == M - 1 && haloR) {
                         uint16_t* h = haloR + ((par ^ 1) * 2 + 0) * Dp + q * 8;
@@ -758,12 +773,13 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
                 int s3 = lx + ymod; if (s3 >= M) s3 -= M;
                 uint16_t* sl = L2b + s3 * Dp;
                 const bool fromHalo = lx == M - 1;
+                const int oa = offA(s3), ob = OB - oa;
                 const uint16_t* src = fromHalo ? halo + (par * 2 + 1) * Dp + q * 8 : sl;
-                ld_state(A, src); ld_state(B, src + OB); mm = fromHalo ? halom[par * 2 + 1] : mb[2 * Mmax + s3];
-                if (firstRow || x == W1 - 1) reset_state2<PAD>(A, B, mm, padA, padB);
+                ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 1] : mb[2 * Mmax + s3];
+                if (PAD && (firstRow || x == W1 - 1)) reset_state2<PAD>(A, B, mm, padA, padB);
                 sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
                 if (active) {
-                    st128(sl, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + OB, make_uint4(B[0], B[1], B[2], B[3]));
+                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
                     if (q == 0) mb[2 * Mmax + s3] = mm;
                     if (lx == 0 && haloL) {
                         uint16_t* h = haloL + ((par ^ 1) * 2 + 1) * Dp + q * 8;
