@@ -37,7 +37,7 @@ CFG = dict(name="cfg2: StereoSGBM MODE_SGBM 5-path, configs/sgbm.yml (numDisp=64
 
 # algorithmic HBM bytes per evaluated cell (x, y, d) of each aggregation-stage kernel in the current pipeline
 # (int16 volumes; images, maps and per-pixel outputs are < 1 % and ignored) -- see DESIGN.md "Kernels"
-KERNEL_BYTES_PER_CELL = {"sgbm_vsum": 2.0, "sgbm_h1": 6.0, "sgbm_vdir": 6.0, "sgbm_h2_wta": 4.0}
+KERNEL_BYTES_PER_CELL = {"sgbm_vsum": 2.0, "sgbm_h1": 6.0, "sgbm_td": 6.0, "sgbm_vdir": 6.0, "sgbm_h2_wta": 4.0}
 PATH_BYTES_PER_CELL = 8.0      # MODE_SGBM aggregation roofline model (C w+r, S_h w+r)
 
 
@@ -48,6 +48,16 @@ def hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic_per_cell():
+    """dram__bytes_read.sum + dram__bytes_write.sum per evaluated cell of each kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_ncu_traffic.json; null when absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_cell"]
+    except Exception:
+        return {}
 
 
 def w1_of(W, p):
@@ -344,8 +354,9 @@ def main():
     dom = max(kern, key=lambda k: kern[k]["ms_total"])
     if dom in KERNEL_BYTES_PER_CELL:
         ach = kern[dom]["algorithmic_GBps"]
+        tpc = measured_traffic_per_cell().get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": (tpc * cells_per_launch if tpc is not None else None), "peak_source": peak_src,
                     "bytes_per_cell": KERNEL_BYTES_PER_CELL[dom], "cells_per_launch": cells_per_launch,
                     "ms_per_launch": kern[dom]["ms_per_launch"], "share_of_step": kern[dom]["share"]}
     else:

@@ -569,7 +569,7 @@ long long mvsv_debug_read(mvsv_ctx* c, int which, void* host, size_t cap)
         case 1: src = c->S; bytes = vol; break;
         case 2: src = c->disp_raw; bytes = img16; break;
         case 3: src = c->VS; bytes = vol; break;
-        case 4: src = c->disp_med; bytes = img16; break;
+        case 4: src = (c->has_sgbm && c->sg.speckleWin > 0) ? c->disp_med : c->disp; bytes = img16; break;
         case 5: src = c->bm_pre[0]; bytes = (size_t)B * c->H * c->pitch; break;
         case 6: src = c->bm_pre[1]; bytes = (size_t)B * c->H * c->pitch; break;
         default: return fail(c, MVSV_ERR_INVALID, "unknown debug buffer");

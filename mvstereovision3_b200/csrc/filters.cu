@@ -172,15 +172,15 @@ __global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__
     atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
 }
 
-__global__ void k_ccl_apply(int16_t* __restrict__ img, const int* __restrict__ label, const int* __restrict__ sizes,
-                            size_t n, int newVal, int maxSize)
+__global__ void k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const int* __restrict__ label,
+                            const int* __restrict__ sizes, size_t n, int newVal, int maxSize)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int l = label[i];
-    if (l < 0) return;
+    if (l < 0) { out[i] = (int16_t)newVal; return; }
     const int root = ccl_find(label, l);          // <= 2 hops after k_ccl_flatten_starts
-    if (sizes[root] <= maxSize) img[i] = (int16_t)newVal;
+    out[i] = (sizes[root] <= maxSize) ? (int16_t)newVal : img[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,7 +263,7 @@ void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
     k_median3<<<grd, blk, 0, c->stream>>>(in, out, c->W, c->H);
 }
 
-void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff)
+void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int newVal, int maxSize, int maxDiff)
 {
     const int W = c->W, H = c->H;
     const size_t n = (size_t)B * W * H;
@@ -278,7 +278,7 @@ void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, i
     }
     { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten_starts<<<grd, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff); }
     { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff); }
-    { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, c->labels, c->sizes, n, newVal, maxSize); }
+    { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, out, c->labels, c->sizes, n, newVal, maxSize); }
 }
 
 void launch_xyz(mvsv_ctx* c, int B)

@@ -127,7 +127,7 @@ void launch_bm(mvsv_ctx* c, int B);
 void launch_xyz(mvsv_ctx* c, int B);
 void launch_means(mvsv_ctx* c, int B);
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
-void launch_speckle(mvsv_ctx* c, int16_t* img, int B, int newVal, int maxSize, int maxDiff);
+void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
 int sgbm_choose_td_cluster(const mvsv_ctx* c);
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);

@@ -1138,7 +1138,10 @@ void launch_sgbm(mvsv_ctx* c, int B)
             default: if (pad) launch_sgbm_g<32, true>(c, B); else launch_sgbm_g<32, false>(c, B); break;
         }
     }
-    launch_median(c, c->disp_raw, c->disp_med, B);
-    cudaMemcpyAsync(c->disp, c->disp_med, npx * sizeof(int16_t), cudaMemcpyDeviceToDevice, c->stream);
-    if (n.speckleWin > 0) launch_speckle(c, c->disp, B, n.INV, n.speckleWin, 16 * n.speckleRange);
+    if (n.speckleWin > 0) {
+        launch_median(c, c->disp_raw, c->disp_med, B);
+        launch_speckle(c, c->disp_med, c->disp, B, n.INV, n.speckleWin, 16 * n.speckleRange);
+    } else {
+        launch_median(c, c->disp_raw, c->disp, B);
+    }
 }

@@ -24,6 +24,9 @@ L = np.stack([l] * B)
 R = np.stack([r] * B)
 with api.Engine(W, H, max_batch=B) as e:
     e.set_sgbm_params(**p)
+    if os.environ.get("MVSV_DBG"):
+        e.debug_set_flags(int(os.environ["MVSV_DBG"], 0))
+        print("debug flags", os.environ["MVSV_DBG"], "td cluster", e.info.sgbm_td_cluster)
     for _ in range(2):
         e.compute(L, R, api.STAGE_SGBM)
         e.sync()
