@@ -110,6 +110,10 @@ int mvsv_compute_device(mvsv_ctx* ctx, const uint8_t* dleft, size_t lstride, con
  *   means : batch x num_rois float */
 int mvsv_download(mvsv_ctx* ctx, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride,
                   float* xyz, float* means);
+/* Utility::calcMinMaxDisparity (src/utility.cpp:287-304) of the last computed maps as a GPU reduction: for every
+ * frame the smallest and largest disparity value > 0, minmax[2*i], minmax[2*i+1]; (0, 0) when a map has none (the
+ * reference dereferences an end iterator there).  Consumed by the PLY writer's grey ramp (src/ply.cpp:62-95). */
+int mvsv_download_minmax(mvsv_ctx* ctx, int16_t* minmax);
 int mvsv_sync(mvsv_ctx* ctx);
 
 int mvsv_get_info(const mvsv_ctx* ctx, mvsv_info* info);

@@ -19,7 +19,7 @@ ABI_SYMBOLS = (
     "mvsv_upload_rectify_maps", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
     "mvsv_compute_device", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
     "mvsv_host_alloc", "mvsv_host_free", "mvsv_debug_set_flags", "mvsv_debug_read",
-    "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
+    "mvsv_download_minmax", "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
 )
 
 
@@ -74,6 +74,7 @@ def load_library():
     lib.mvsv_compute_device.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint]
     lib.mvsv_download.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
     lib.mvsv_sync.argtypes = [vp]
+    lib.mvsv_download_minmax.argtypes = [vp, vp]
     lib.mvsv_get_info.argtypes = [vp, C.POINTER(Info)]
     lib.mvsv_stream.argtypes = [vp]
     lib.mvsv_stream.restype = vp
@@ -248,6 +249,12 @@ class Engine:
         if means:
             res["means"] = mn
         return res
+
+    def download_minmax(self, batch):
+        """Utility::calcMinMaxDisparity (reference src/utility.cpp:287-304) per frame, reduced on the GPU."""
+        mm = np.empty((batch, 2), np.int16)
+        self._ck(self._lib.mvsv_download_minmax(self._ctx, mm.ctypes.data))
+        return mm
 
     # -- timing ---------------------------------------------------------------------------------
     def timer_start(self):

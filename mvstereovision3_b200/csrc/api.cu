@@ -8,7 +8,7 @@
 
 const char* const kKernelNames[KID_COUNT] = {
     "remap", "sgbm_prefilter", "sgbm_vsum", "sgbm_h1", "sgbm_vdir", "sgbm_td", "sgbm_h2_wta", "median3", "ccl_rows", "ccl_vmerge",
-    "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill"};
+    "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill", "minmax"};
 
 namespace {
 
@@ -43,7 +43,7 @@ void free_images(mvsv_ctx* c)
     for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->bm_pre[i]); }
     dfree(c->recL);
     dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
-    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means);
+    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means); dfree(c->minmax);
 }
 void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); dfree(c->plR); c->vol_elems = 0; }
 void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
@@ -464,6 +464,26 @@ int mvsv_download(mvsv_ctx* c, int16_t* disp, size_t dstride, uint8_t* rectL, ui
         MVSV_CK(c, cudaMemcpyAsync(means, c->means, (size_t)B * c->nrois * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
     MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    return MVSV_OK;
+}
+
+int mvsv_download_minmax(mvsv_ctx* c, int16_t* minmax)
+{
+    if (!c || !minmax) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    const int B = c->lastB;
+    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
+    if (!c->minmax) MVSV_CK(c, cudaMalloc(&c->minmax, (size_t)c->maxB * 2 * sizeof(int)));
+    launch_minmax(c, B);
+    std::vector<int> h((size_t)2 * B);
+    MVSV_CK(c, cudaMemcpyAsync(h.data(), c->minmax, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < B; ++i) {
+        const bool none = h[2 * i + 1] <= 0;
+        minmax[2 * i] = none ? 0 : (int16_t)h[2 * i];
+        minmax[2 * i + 1] = none ? 0 : (int16_t)h[2 * i + 1];
+    }
     return MVSV_OK;
 }
 

@@ -238,7 +238,39 @@ __global__ void k_means(const int16_t* __restrict__ disp, const int* __restrict_
     }
 }
 
+__global__ void k_minmax_init(int* mm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mm[i] = (i & 1) ? -32768 : 32767;
+}
+__global__ void k_minmax(const int16_t* __restrict__ disp, int* __restrict__ mm, int npx)
+{
+    const int16_t* img = disp + (size_t)blockIdx.y * npx;
+    int lo = 32767, hi = -32768;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const int v = img[i];
+        if (v > 0) { lo = min(lo, v); hi = max(hi, v); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi > 0) {
+        atomicMin(&mm[2 * blockIdx.y], lo);
+        atomicMax(&mm[2 * blockIdx.y + 1], hi);
+    }
+}
+
 }  // namespace
+
+void launch_minmax(mvsv_ctx* c, int B)
+{
+    { KernelTimer kt(c, KID_MINMAX); k_minmax_init<<<(2 * B + 127) / 128, 128, 0, c->stream>>>(c->minmax, 2 * B); }
+    dim3 grd(32, B);
+    KernelTimer kt(c, KID_MINMAX);
+    k_minmax<<<grd, 256, 0, c->stream>>>(c->disp, c->minmax, c->W * c->H);
+}
 
 void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t strideElems)
 {

@@ -29,7 +29,7 @@ struct BmNorm {
 enum KernelId {
     KID_REMAP = 0, KID_SGBM_PREFILTER, KID_SGBM_VSUM, KID_SGBM_H1, KID_SGBM_VDIR, KID_SGBM_TD, KID_SGBM_H2_WTA, KID_MEDIAN,
     KID_CCL_ROWS, KID_CCL_VMERGE, KID_CCL_FLATTEN, KID_CCL_APPLY, KID_BM_PREFILTER, KID_BM_TEX, KID_BM_COLSUM,
-    KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_COUNT
+    KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_MINMAX, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -94,6 +94,7 @@ struct mvsv_ctx {
     int nrois = 0;
     int* rois = nullptr;                      // device [n][4]
     float* means = nullptr;                   // device [B][n]
+    int* minmax = nullptr;                    // device [B][2]
 
     // pinned staging for pageable host buffers
     uint8_t* stage = nullptr;
@@ -126,6 +127,7 @@ void launch_sgbm(mvsv_ctx* c, int B);
 void launch_bm(mvsv_ctx* c, int B);
 void launch_xyz(mvsv_ctx* c, int B);
 void launch_means(mvsv_ctx* c, int B);
+void launch_minmax(mvsv_ctx* c, int B);
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
 void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
