@@ -260,6 +260,7 @@ int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    c->num_sms = prop.multiProcessorCount;
     if (prop.major < 10) {
         g_init_error = "mvsv_init: kernels are built for sm_100a only";
         mvsv_destroy(c);

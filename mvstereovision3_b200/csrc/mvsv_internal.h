@@ -64,7 +64,9 @@ struct mvsv_ctx {
     bool has_sgbm = false, has_bm = false;
     mvsv_sgbm_params sgbm_raw{};
     SgbmNorm sg{};
-    int td_nc = 0;               // cluster size of the fused previous-row sweep (0: independent passes)
+    int td_nc = 0;               // smallest cluster size of the fused previous-row sweep that fits (0: independent passes)
+    unsigned td_nc_mask = 0;     // all cluster sizes that fit (bit = size)
+    int num_sms = 148;
     mvsv_bm_params bm_raw{};
     BmNorm bm{};
 
@@ -131,7 +133,7 @@ void launch_minmax(mvsv_ctx* c, int B);
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
 void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
-int sgbm_choose_td_cluster(const mvsv_ctx* c);
+int sgbm_choose_td_cluster(mvsv_ctx* c);
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);
 
 #ifdef __CUDACC__

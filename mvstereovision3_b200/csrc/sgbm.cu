@@ -985,7 +985,11 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
     { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16, st>>>(a); }
-    const int nc = c->td_nc;
+    // throughput: the smallest cluster that fits (clusters of 2 pack the SMs exactly); small batches: more CTAs per
+    // frame as long as the whole grid is still resident at once (single-pair latency 3.3 -> 2.2 ms at cfg 2)
+    int nc = c->td_nc;
+    if (nc > 0 && !((c->debug_flags >> 8) & 0xff))
+        while (((unsigned)(nc << 1) & c->td_nc_mask) && (long long)B * (nc << 1) <= c->num_sms) nc <<= 1;
     auto vdirs = [&](int bottomUp) {
         if (nc > 0) {
             TdArgs t;
@@ -1082,12 +1086,14 @@ cudaError_t sgbm_configure_kernels()
 // Cluster size for the fused previous-row sweep: the smallest power of two whose column strip fits in shared
 // memory (clusters of 2 pack the 148 SMs exactly; clusters of 4 strand 16 of them, measured).
 // 0 = does not fit (or clusters unavailable): fall back to the three independent k_sgbm_vdir passes.
-int sgbm_choose_td_cluster(const mvsv_ctx* c)
+int sgbm_choose_td_cluster(mvsv_ctx* c)
 {
     const SgbmNorm& n = c->sg;
+    c->td_nc_mask = 0;
     if (n.W1 <= 0) return 0;
     const int forced = (int)((c->debug_flags >> 8) & 0xff);
     if (forced == 0xff) return 0;
+    int smallest = 0;
     // clusters of 16 (non-portable) fit only a handful at a time: measured slower than the independent passes,
     // which run at 95 % of HBM peak, so they are used only when forced by the test hook
     for (int nc = 1; nc <= 16; nc <<= 1) {
@@ -1106,9 +1112,12 @@ int sgbm_choose_td_cluster(const mvsv_ctx* c)
             case 16: ok = td_max_clusters<16>(nc, smem, Mmax); break;
             default: ok = td_max_clusters<32>(nc, smem, Mmax); break;
         }
-        if (ok > 0) return nc;
+        if (ok > 0) {
+            c->td_nc_mask |= (unsigned)nc;
+            if (!smallest) smallest = nc;
+        }
     }
-    return 0;
+    return smallest;
 }
 
 // Geometry of the reversed right-image planes for the cost kernel (see k_sgbm_prefilter / k_sgbm_vsum).
