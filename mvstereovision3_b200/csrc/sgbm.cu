@@ -18,7 +18,9 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int VS_THREADS = 256;
+// compute threads of the cost kernel: 256, or 512 when a pixel needs >= 16 lanes (D > 64), so that the staging of
+// the right-image entries (PX - 1 + Dp per row) is amortised over more columns
+constexpr int vs_compute_threads(int G) { return G >= 16 ? 512 : 256; }
 
 // ------------------------------------------------------------------------------------------------
 // K2a: prefilter (A.2: sob/raw channels with ftzero borders, lo/hi half-sample bounds).
@@ -113,17 +115,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int VS_RD = 4;       // raw-ring depth of the cost kernel's producer (rows in flight + 1)
 
-// geometry fixed by G: entries a CTA can touch, 8-entry vectors per channel (power of two), producer warps
+// geometry fixed by G: entries a CTA can touch, 8-entry vectors per channel, producer warps
 template <int G> struct VsGeom {
-    static constexpr int PX = VS_THREADS / G;
+    static constexpr int CT = vs_compute_threads(G);
+    static constexpr int PX = CT / G;
     static constexpr int NE = PX - 1 + 8 * G;
-    static constexpr int NV = (NE + 2 <= 16) ? 2 : (NE + 2 <= 32) ? 4 : (NE + 2 <= 64) ? 8 : (NE + 2 <= 128) ? 16 : (NE + 2 <= 256) ? 32 : 64;
+    static constexpr int NV = (NE + 2 + 7) / 8;                // one spare entry pair for the odd copies
     static constexpr int ITEMS = 6 * NV;                       // (channel, vector) staging items per row
     static constexpr int NPW = (ITEMS + 95) / 96;              // producer warps: <= 3 items per producer lane
     static constexpr int NPT = 32 * NPW;                       // producer threads
     static constexpr int IPL = (ITEMS + NPT - 1) / NPT;        // items per producer lane
     static constexpr int RPL = (PX + NPT - 1) / NPT;           // left records per producer lane
-    static constexpr int THREADS = VS_THREADS + NPT;
+    static constexpr int THREADS = CT + NPT;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
     using GE = VsGeom<G>;
     constexpr int PX = GE::PX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: sR[2 buf][6][8][LEN] u16 | sL[2 buf][PX][12] u32 | ring[bs][VS_THREADS] (uint2 if the pixel cost
+    // layout: sR[2 buf][6][8][LEN] u16 | sL[2 buf][PX][12] u32 | ring[bs][CT] (uint2 if the pixel cost
     // fits a byte -- 2*ftzero+63 <= 255 -- else uint4)
     uint16_t* sR = reinterpret_cast<uint16_t*>(smem_raw);
     unsigned* sL = reinterpret_cast<unsigned*>(sR + (size_t)2 * 6 * 8 * a.LEN);
@@ -150,14 +153,15 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
     // named barriers: 1 + buf = "stage buf is full", 3 + buf = "stage buf is free again"
     constexpr int NTH = GE::THREADS;
 
-    if (tid >= VS_THREADS) {
+    constexpr int CT = GE::CT;
+    if (tid >= CT) {
         // ===================== producer warps: stage row t while the compute warps consume row t-1 ===============
         // Global loads run VS_RD-1 rows ahead through cp.async into a private raw ring (every lane reads back only
         // what it copied), so the producer's critical path is LDS -> funnel shifts -> STS.
-        const int pt = tid - VS_THREADS;
+        const int pt = tid - CT;
         const int xr_max = xa + PX - 1 + a.minX1 - a.minD;       // entry e <-> right column xr_max - e
         const int j0 = a.JOFF + a.W - 1 - xr_max;                // reversed-plane index of entry 0 (multiple of 8)
-        uint4* rawPQ = reinterpret_cast<uint4*>(ring + (size_t)bs * VS_THREADS * (R8 ? 8 : 16));   // [VS_RD][IPL][2][NPT]
+        uint4* rawPQ = reinterpret_cast<uint4*>(ring + (size_t)bs * CT * (R8 ? 8 : 16));   // [VS_RD][IPL][2][NPT]
         uint2* rawL = reinterpret_cast<uint2*>(rawPQ + VS_RD * GE::IPL * 2 * GE::NPT);             // [VS_RD][RPL][NPT]
         size_t srcOff[GE::IPL]; int dstOff[GE::IPL]; bool itemOn[GE::IPL];
 #pragma unroll
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
 #undef MVSV_PIX
             uint4 old = make_uint4(0, 0, 0, 0);
             if (R8) {
-                uint2* rs = reinterpret_cast<uint2*>(ring) + (size_t)slot * VS_THREADS + tid;
+                uint2* rs = reinterpret_cast<uint2*>(ring) + (size_t)slot * CT + tid;
                 if (t >= bs) {
                     const uint2 o = *rs;
                     old = make_uint4(__byte_perm(o.x, 0, 0x4140), __byte_perm(o.x, 0, 0x4342), __byte_perm(o.y, 0, 0x4140),
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
                 }
                 *rs = make_uint2(__byte_perm(pix.x, pix.y, 0x6420), __byte_perm(pix.z, pix.w, 0x6420));
             } else {
-                uint4* rs = reinterpret_cast<uint4*>(ring) + (size_t)slot * VS_THREADS + tid;
+                uint4* rs = reinterpret_cast<uint4*>(ring) + (size_t)slot * CT + tid;
                 if (t >= bs) old = *rs;
                 *rs = pix;
             }
@@ -363,7 +367,7 @@ struct AggArgs {
 // The row scans stream their operands through a per-lane shared-memory ring filled by cp.async (LDGSTS): the
 // loads of the next PFD steps are in flight without holding registers.  Each lane only ever reads back the 16
 // bytes it copied itself, so cp.async.wait_group is the only synchronisation needed.
-constexpr int H1_PFD = 4;
+constexpr int H1_PFD = 8;
 constexpr int HPF = 2;         // k_sgbm_h2_wta is issue-bound: it keeps a cheap 2-step register prefetch instead
 
 
@@ -960,7 +964,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
                                               planeStrideR, c->vsRP, c->vsJOFF);
     }
     {
-        constexpr int PX = VS_THREADS / G;
+        constexpr int PX = VsGeom<G>::PX;
         VsArgs a;
         a.recL = c->recL; a.plR = c->plR; a.planeStrideR = planeStrideR;
         a.VS = c->VS; a.W = c->W; a.H = c->H; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.minD = n.minD; a.minX1 = n.minX1;
@@ -968,7 +972,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         const bool r8 = 2 * n.ftzero + 63 <= 255;
         using GE = VsGeom<G>;
         const size_t smem = (size_t)2 * 6 * 8 * a.LEN * 2 + (size_t)2 * PX * 12 * 4 +
-                            (size_t)(2 * n.SH2 + 1) * VS_THREADS * (r8 ? 8 : 16) +
+                            (size_t)(2 * n.SH2 + 1) * GE::CT * (r8 ? 8 : 16) +
                             (size_t)VS_RD * GE::IPL * 2 * GE::NPT * 16 + (size_t)VS_RD * GE::RPL * GE::NPT * 8;
         dim3 grd((n.W1 + PX - 1) / PX, B);
         KernelTimer kt(c, KID_SGBM_VSUM);
@@ -1123,10 +1127,9 @@ int sgbm_choose_td_cluster(mvsv_ctx* c)
 // Geometry of the reversed right-image planes for the cost kernel (see k_sgbm_prefilter / k_sgbm_vsum).
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF)
 {
-    const int PX = VS_THREADS / n.G;
+    const int PX = vs_compute_threads(n.G) / n.G;
     const int NE = PX - 1 + n.Dp;                    // entries a CTA can touch
-    int nv = 2;
-    while (nv * 8 < NE + 2) nv <<= 1;                // power of two, one spare vector for the odd copies
+    const int nv = (NE + 2 + 7) / 8;                 // == VsGeom<G>::NV
     const int K = W - PX - n.minX1 + n.minD;         // j0 = JOFF + K - xa must be a multiple of 8 (xa is)
     const int joff = PX + 8 + (((8 - ((PX + 8 + K) % 8)) % 8 + 8) % 8);
     *NV = nv; *JOFF = joff; *RP = (joff + W + nv * 8 + 16 + 7) / 8 * 8;

@@ -307,3 +307,15 @@ def test_cpp_mirror_end_to_end(oracle, tmp_path):
                            str(tmp_path / "out.raw")])
     got = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.int16).reshape(H, W)
     check("cpp mirror", got, oracle.sgbm(l, r, CFG2_SHIPPED))
+
+
+def test_d256_large_block_fits_shared_memory(oracle):
+    """D = 256 with the largest block size the contract allows (bs 11: 121*93 + P2 <= 32767) -- the cost kernel's
+    shared-memory footprint (staging copies + row ring + producer ring) is at its maximum here."""
+    p = cases.sgbm_params(numDisp=256, blockSize=11, P1=8, P2=32, uniquenessRatio=5)
+    H, W = 30, 300
+    l, r = synth.random_pair(H, W, seed=77)
+    with api.Engine(W, H) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(l, r, api.STAGE_SGBM)
+        check("d256 bs11", e.download(1)["disp"][0], oracle.sgbm(l, r, p))
