@@ -310,23 +310,28 @@ template <int G, bool PAD>
 __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const uint4& C, unsigned P1P1, unsigned P2P2,
                                          int q, bool padLane)
 {
-    unsigned up = MVSV_PK_MAX, dn = MVSV_PK_MAX;
+    // min(min(Lp[k-1], Lp[k+1]) + P1, Lp[k], m + P2) == min3(Lp[k-1] + P1, Lp[k+1] + P1, min(Lp[k], m + P2)):
+    // P1 is added once per register with a plain 32-bit add (no carry between the halves: L + P1 < 65536), which
+    // issues at full rate, and one VIMNMX3 replaces a VIMNMX + VIADDMNMX pair on the half-rate DPX pipe.
+    const unsigned P0 = L[0] + P1P1, P3 = L[3] + P1P1;
+    unsigned up = 0xffffffffu, dn = 0xffffffffu;        // out-of-range neighbour: larger than any L + P1
     if (G > 1) {
-        const unsigned u = __shfl_up_sync(FULL, L[3], 1, G);
-        const unsigned d = __shfl_down_sync(FULL, L[0], 1, G);
+        const unsigned u = __shfl_up_sync(FULL, P3, 1, G);
+        const unsigned d = __shfl_down_sync(FULL, P0, 1, G);
         if (q != 0) up = u;
         if (q != G - 1) dn = d;
     }
-    const unsigned X0 = __byte_perm(up, L[0], 0x5432);
-    const unsigned X1 = __byte_perm(L[0], L[1], 0x5432);
-    const unsigned X2 = __byte_perm(L[1], L[2], 0x5432);
-    const unsigned X3 = __byte_perm(L[2], L[3], 0x5432);
-    const unsigned X4 = __byte_perm(L[3], dn, 0x5432);
-    const unsigned mP2 = __vadd2(mm, P2P2);
-    unsigned n0 = __vminu2(__viaddmin_u16x2(__vminu2(X0, X1), P1P1, L[0]), mP2) + C.x - mm;
-    unsigned n1 = __vminu2(__viaddmin_u16x2(__vminu2(X1, X2), P1P1, L[1]), mP2) + C.y - mm;
-    unsigned n2 = __vminu2(__viaddmin_u16x2(__vminu2(X2, X3), P1P1, L[2]), mP2) + C.z - mm;
-    unsigned n3 = __vminu2(__viaddmin_u16x2(__vminu2(X3, X4), P1P1, L[3]), mP2) + C.w - mm;
+    const unsigned Q1 = L[1] + P1P1, Q2 = L[2] + P1P1;
+    const unsigned X0 = __byte_perm(up, P0, 0x5432);
+    const unsigned X1 = __byte_perm(P0, Q1, 0x5432);
+    const unsigned X2 = __byte_perm(Q1, Q2, 0x5432);
+    const unsigned X3 = __byte_perm(Q2, P3, 0x5432);
+    const unsigned X4 = __byte_perm(P3, dn, 0x5432);
+    const unsigned mP2 = mm + P2P2;
+    unsigned n0 = __vimin3_u16x2(X0, X1, __vminu2(L[0], mP2)) + C.x - mm;
+    unsigned n1 = __vimin3_u16x2(X1, X2, __vminu2(L[1], mP2)) + C.y - mm;
+    unsigned n2 = __vimin3_u16x2(X2, X3, __vminu2(L[2], mP2)) + C.z - mm;
+    unsigned n3 = __vimin3_u16x2(X3, X4, __vminu2(L[3], mP2)) + C.w - mm;
     if (PAD && padLane) { n0 = n1 = n2 = n3 = MVSV_PK_MAX; }
     unsigned m = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);
 #pragma unroll
@@ -613,35 +618,38 @@ template <int G2, bool PAD>
 __device__ __forceinline__ void sgm_step2(unsigned (&A)[4], unsigned (&B)[4], unsigned& mm, const uint4& Ca, const uint4& Cb,
                                           unsigned P1P1, unsigned P2P2, int q, bool padA, bool padB)
 {
-    unsigned upA = MVSV_PK_MAX, dnA, upB, dnB = MVSV_PK_MAX;
+    // see sgm_step: neighbours are taken from L + P1 (plain adds), one VIMNMX3 per register
+    const unsigned pa0 = A[0] + P1P1, pa1 = A[1] + P1P1, pa2 = A[2] + P1P1, pa3 = A[3] + P1P1;
+    const unsigned pb0 = B[0] + P1P1, pb1 = B[1] + P1P1, pb2 = B[2] + P1P1, pb3 = B[3] + P1P1;
+    unsigned upA = 0xffffffffu, dnA, upB, dnB = 0xffffffffu;
     if (G2 > 1) {
         const int nxt = (q + 1) & (G2 - 1), prv = (q + G2 - 1) & (G2 - 1);
-        const unsigned x = __shfl_sync(FULL, B[0], nxt, G2);     // bottom of octet (q+1)+G2; lane G2-1 gets octet G2
-        const unsigned y = __shfl_sync(FULL, A[0], nxt, G2);     // bottom of octet q+1
-        const unsigned u = __shfl_sync(FULL, A[3], prv, G2);     // top of octet q-1; lane 0 gets octet G2-1
-        const unsigned w = __shfl_sync(FULL, B[3], prv, G2);     // top of octet q-1+G2
+        const unsigned x = __shfl_sync(FULL, pb0, nxt, G2);     // bottom of octet (q+1)+G2; lane G2-1 gets octet G2
+        const unsigned y = __shfl_sync(FULL, pa0, nxt, G2);     // bottom of octet q+1
+        const unsigned u = __shfl_sync(FULL, pa3, prv, G2);     // top of octet q-1; lane 0 gets octet G2-1
+        const unsigned w = __shfl_sync(FULL, pb3, prv, G2);     // top of octet q-1+G2
         dnA = (q == G2 - 1) ? x : y;
         if (q != G2 - 1) dnB = x;
         if (q != 0) upA = u;
         upB = (q == 0) ? u : w;
     } else {
-        dnA = B[0]; upB = A[3];
+        dnA = pb0; upB = pa3;
     }
-    const unsigned mP2 = __vadd2(mm, P2P2);
-    const unsigned XA0 = __byte_perm(upA, A[0], 0x5432), XA1 = __byte_perm(A[0], A[1], 0x5432);
-    const unsigned XA2 = __byte_perm(A[1], A[2], 0x5432), XA3 = __byte_perm(A[2], A[3], 0x5432);
-    const unsigned XA4 = __byte_perm(A[3], dnA, 0x5432);
-    const unsigned XB0 = __byte_perm(upB, B[0], 0x5432), XB1 = __byte_perm(B[0], B[1], 0x5432);
-    const unsigned XB2 = __byte_perm(B[1], B[2], 0x5432), XB3 = __byte_perm(B[2], B[3], 0x5432);
-    const unsigned XB4 = __byte_perm(B[3], dnB, 0x5432);
-    unsigned a0 = __vminu2(__viaddmin_u16x2(__vminu2(XA0, XA1), P1P1, A[0]), mP2) + Ca.x - mm;
-    unsigned a1 = __vminu2(__viaddmin_u16x2(__vminu2(XA1, XA2), P1P1, A[1]), mP2) + Ca.y - mm;
-    unsigned a2 = __vminu2(__viaddmin_u16x2(__vminu2(XA2, XA3), P1P1, A[2]), mP2) + Ca.z - mm;
-    unsigned a3 = __vminu2(__viaddmin_u16x2(__vminu2(XA3, XA4), P1P1, A[3]), mP2) + Ca.w - mm;
-    unsigned b0 = __vminu2(__viaddmin_u16x2(__vminu2(XB0, XB1), P1P1, B[0]), mP2) + Cb.x - mm;
-    unsigned b1 = __vminu2(__viaddmin_u16x2(__vminu2(XB1, XB2), P1P1, B[1]), mP2) + Cb.y - mm;
-    unsigned b2 = __vminu2(__viaddmin_u16x2(__vminu2(XB2, XB3), P1P1, B[2]), mP2) + Cb.z - mm;
-    unsigned b3 = __vminu2(__viaddmin_u16x2(__vminu2(XB3, XB4), P1P1, B[3]), mP2) + Cb.w - mm;
+    const unsigned mP2 = mm + P2P2;
+    const unsigned XA0 = __byte_perm(upA, pa0, 0x5432), XA1 = __byte_perm(pa0, pa1, 0x5432);
+    const unsigned XA2 = __byte_perm(pa1, pa2, 0x5432), XA3 = __byte_perm(pa2, pa3, 0x5432);
+    const unsigned XA4 = __byte_perm(pa3, dnA, 0x5432);
+    const unsigned XB0 = __byte_perm(upB, pb0, 0x5432), XB1 = __byte_perm(pb0, pb1, 0x5432);
+    const unsigned XB2 = __byte_perm(pb1, pb2, 0x5432), XB3 = __byte_perm(pb2, pb3, 0x5432);
+    const unsigned XB4 = __byte_perm(pb3, dnB, 0x5432);
+    unsigned a0 = __vimin3_u16x2(XA0, XA1, __vminu2(A[0], mP2)) + Ca.x - mm;
+    unsigned a1 = __vimin3_u16x2(XA1, XA2, __vminu2(A[1], mP2)) + Ca.y - mm;
+    unsigned a2 = __vimin3_u16x2(XA2, XA3, __vminu2(A[2], mP2)) + Ca.z - mm;
+    unsigned a3 = __vimin3_u16x2(XA3, XA4, __vminu2(A[3], mP2)) + Ca.w - mm;
+    unsigned b0 = __vimin3_u16x2(XB0, XB1, __vminu2(B[0], mP2)) + Cb.x - mm;
+    unsigned b1 = __vimin3_u16x2(XB1, XB2, __vminu2(B[1], mP2)) + Cb.y - mm;
+    unsigned b2 = __vimin3_u16x2(XB2, XB3, __vminu2(B[2], mP2)) + Cb.z - mm;
+    unsigned b3 = __vimin3_u16x2(XB3, XB4, __vminu2(B[3], mP2)) + Cb.w - mm;
     if (PAD && padA) { a0 = a1 = a2 = a3 = MVSV_PK_MAX; }
     if (PAD && padB) { b0 = b1 = b2 = b3 = MVSV_PK_MAX; }
     unsigned m = __vimin3_u16x2(__vimin3_u16x2(a0, a1, a2), __vimin3_u16x2(a3, b0, b1), __vimin3_u16x2(b2, b3, b3));
