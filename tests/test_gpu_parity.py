@@ -319,3 +319,15 @@ def test_d256_large_block_fits_shared_memory(oracle):
         e.set_sgbm_params(**gpu_params(p))
         e.compute(l, r, api.STAGE_SGBM)
         check("d256 bs11", e.download(1)["disp"][0], oracle.sgbm(l, r, p))
+
+
+def test_worst_case_cost_kernel_footprint(oracle):
+    """The parameter set with the largest shared-memory footprint of the cost kernel inside the contract:
+    D = 256, preFilterCap 97 (pixel cost no longer fits a byte -> 16-bit row ring), blockSize 11."""
+    p = cases.sgbm_params(numDisp=256, blockSize=11, P1=8, P2=32, preFilterCap=97)
+    H, W = 28, 290
+    l, r = synth.random_pair(H, W, seed=78)
+    with api.Engine(W, H) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.compute(l, r, api.STAGE_SGBM)
+        check("d256 cap97 bs11", e.download(1)["disp"][0], oracle.sgbm(l, r, p))
