@@ -1,0 +1,91 @@
+"""Randomised parity (hypothesis): random in-contract StereoSGBM / StereoBM parameters and image shapes.
+CPU: the C oracle against cv2 4.13.0.  GPU: the CUDA path (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import cases
+from mvstereovision3_b200 import synth
+
+
+@st.composite
+def sgbm_case(draw, max_d=64):
+    num_disp = draw(st.sampled_from([d for d in (8, 16, 24, 32, 40, 48, 64, 96, 128) if d <= max_d]))
+    min_disp = draw(st.integers(-3, 4))
+    bs = draw(st.integers(1, 11))
+    cap = draw(st.sampled_from([0, 7, 15, 31, 63]))
+    ftzero = max(cap, 15) | 1
+    eff = 2 * (bs // 2) + 1
+    budget = 32767 - eff * eff * (2 * ftzero + 63)
+    p1 = draw(st.integers(0, 60))
+    p2 = draw(st.integers(0, max(0, min(budget, 2000))))
+    if max(p2 if p2 > 0 else 5, (p1 if p1 > 0 else 2) + 1) > budget:
+        p1, p2 = 0, 0
+    p = cases.sgbm_params(minDisp=min_disp, numDisp=num_disp, blockSize=bs, P1=p1, P2=p2, preFilterCap=cap,
+                          uniquenessRatio=draw(st.sampled_from([-1, 0, 5, 10, 25])),
+                          disp12MaxDiff=draw(st.integers(-1, 4)),
+                          speckleWindowSize=draw(st.sampled_from([0, 0, 20, 150])),
+                          speckleRange=draw(st.integers(0, 3)), mode=draw(st.integers(0, 1)))
+    H = draw(st.integers(12, 44))
+    W = draw(st.integers(max(num_disp + abs(min_disp) + 6, 24), num_disp + 110))
+    seed = draw(st.integers(0, 2 ** 16))
+    kind = draw(st.sampled_from(["ramp", "noise"]))
+    return p, H, W, seed, kind
+
+
+def make_pair(p, H, W, seed, kind):
+    if kind == "ramp":
+        l, r, _ = synth.stereogram(H, W, max(p["minDisp"], 0), p["numDisp"], seed=seed)
+        return l, r
+    return synth.random_pair(H, W, seed=seed)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(sgbm_case())
+def test_oracle_vs_cv2_random(oracle, case):
+    cv2 = pytest.importorskip("cv2")
+    p, H, W, seed, kind = case
+    l, r = make_pair(p, H, W, seed, kind)
+    m = cv2.StereoSGBM_create(minDisparity=p["minDisp"], numDisparities=p["numDisp"], blockSize=p["blockSize"],
+                              P1=p["P1"], P2=p["P2"], disp12MaxDiff=p["disp12MaxDiff"], preFilterCap=p["preFilterCap"],
+                              uniquenessRatio=p["uniquenessRatio"], speckleWindowSize=p["speckleWindowSize"],
+                              speckleRange=p["speckleRange"],
+                              mode=cv2.STEREO_SGBM_MODE_HH if p["mode"] == 1 else cv2.STEREO_SGBM_MODE_SGBM)
+    np.testing.assert_array_equal(oracle.sgbm(l, r, p), m.compute(l, r))
+
+
+@pytest.mark.gpu
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+@given(sgbm_case(max_d=128))
+def test_cuda_vs_oracle_random(oracle, case):
+    from mvstereovision3_b200 import api
+    p, H, W, seed, kind = case
+    l, r = make_pair(p, H, W, seed, kind)
+    gp = dict(p)
+    gp["disparityMode"] = gp.pop("mode")
+    with api.Engine(W, H) as e:
+        e.set_sgbm_params(**gp)
+        e.compute(l, r, api.STAGE_SGBM)
+        got = e.download(1)["disp"][0]
+    want = oracle.sgbm(l, r, p)
+    assert np.array_equal(got, want), (p, H, W, seed, kind, int((got != want).sum()))
+
+
+@pytest.mark.gpu
+@settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.sampled_from([16, 32, 48, 64, 80]), st.sampled_from([5, 7, 9, 15, 21]), st.integers(1, 63),
+       st.sampled_from([0, 5, 15]), st.sampled_from([0, 10, 60]), st.integers(30, 60), st.integers(0, 999))
+def test_cuda_bm_vs_oracle_random(oracle, nd, bs, cap, uniq, tex, H, seed):
+    from mvstereovision3_b200 import api
+    if bs * bs * 2 * cap > 65535:
+        cap = 65535 // (2 * bs * bs)
+    W = nd + bs + 40
+    H = max(H, bs + 8)
+    l, r, _ = synth.stereogram(H, W, 0, nd, seed=seed)
+    p = dict(numDisp=nd, blockSize=bs, preFilterCap=cap, textureThreshold=tex, uniquenessRatio=uniq)
+    with api.Engine(W, H) as e:
+        e.set_bm_params(**p)
+        e.compute(l, r, api.STAGE_BM)
+        got = e.download(1)["disp"][0]
+    want = oracle.bm(l, r, p)
+    assert np.array_equal(got, want), (p, H, W, seed, int((got != want).sum()))
