@@ -479,6 +479,11 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
 // The C/S vectors of the next work item (also across the row barrier) are prefetched into registers.
 constexpr int TD_THREADS = 512;
 constexpr int TD_SMEM_LIMIT = 200 * 1024;
+// byte offset of the six halo mbarriers behind L | halo[3][2] | m | halom[3][2] (rounded up to 16)
+__host__ __device__ inline size_t td_bar_offset(int Mmax, int Dp)
+{
+    return (((size_t)3 * Mmax * Dp * 2 + (size_t)6 * Dp * 2 + (size_t)3 * Mmax * 4 + 6 * 4) + 15) / 16 * 16;
+}
 
 struct TdArgs {
     const uint16_t* C; uint16_t* S;
@@ -669,6 +674,47 @@ __device__ __forceinline__ void reset_state2(unsigned (&A)[4], unsigned (&B)[4],
     mm = 0u;
 }
 
+// ---- point-to-point halo hand-off between the CTAs of a cluster: asynchronous remote stores (st.async) that
+// complete a transaction count on an mbarrier in the RECEIVER's shared memory.  Only the lane group that needs a
+// halo ever waits; there is no cluster-wide barrier (and no release fence over outstanding global stores) in the
+// row loop.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned cta)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(unsigned raddr, const uint4& v, unsigned rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_b32(unsigned raddr, unsigned v, unsigned rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+
 // K3b'' -- the fused previous-row sweep (see k_sgbm_td above for the scheme) with 16 disparities per lane.
 constexpr int TD2_THREADS = 512;      // launch bound; the launcher picks 256 or 512 threads per CTA
 
@@ -677,7 +723,9 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
 {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: L[3][Mmax][Dp] u16 | halo[2 parity][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[2][2] u32
+    // layout: L[3][Mmax][Dp] u16 | halo[3 slots][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[3][2] u32 | bars[3][2] u64
+    // Halo slots are triple buffered (row y reads slot y % 3, a sender in row y fills slot (y+1) % 3): a neighbour
+    // can be at most one row ahead, so the slot it fills is never the one still being read.
     constexpr int Dp = 16 * G2;                     // == a.Dp
     constexpr int OB = 8 * G2;                      // element offset of the lane's second octet
     // Bank-conflict swizzle of the state slots: a quarter-warp phase (8 lanes) covers 8/G2 pixels that each touch
@@ -688,8 +736,10 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
     auto offA = [&](int slot) { return (SWS >= 0 && ((slot >> (SWS < 0 ? 0 : SWS)) & 1)) ? OB : 0; };
     uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* halo = Lb + (size_t)3 * a.Mmax * Dp;
-    unsigned* mb = reinterpret_cast<unsigned*>(halo + 4 * Dp);
+    unsigned* mb = reinterpret_cast<unsigned*>(halo + 6 * Dp);
     unsigned* halom = mb + 3 * a.Mmax;
+    // bars[slot][dir]: completes when the halo of that slot/direction has fully arrived (16-byte aligned region)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + td_bar_offset(a.Mmax, Dp));
 
     const int r = (int)cluster.block_rank();
     const int f = blockIdx.y;
@@ -698,10 +748,12 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
     const int NG = blockDim.x / G2;
     const int g = threadIdx.x / G2, q = threadIdx.x % G2;
     const bool padA = q * 8 >= a.D, padB = (q + G2) * 8 >= a.D;
-    uint16_t* haloR = (r + 1 < a.NC) ? cluster.map_shared_rank(halo, r + 1) : nullptr;   // CTA owning columns x1..
-    uint16_t* haloL = (r > 0) ? cluster.map_shared_rank(halo, r - 1) : nullptr;
-    unsigned* halomR = (r + 1 < a.NC) ? cluster.map_shared_rank(halom, r + 1) : nullptr;
-    unsigned* halomL = (r > 0) ? cluster.map_shared_rank(halom, r - 1) : nullptr;
+    const bool hasL = r > 0, hasR = r + 1 < a.NC;
+    // shared::cluster addresses of the neighbours' halo / halom / mbarrier arrays (same layout in every CTA)
+    const unsigned rHalo = hasR ? mapa_u32(smem_u32(halo), r + 1) : 0u, lHalo = hasL ? mapa_u32(smem_u32(halo), r - 1) : 0u;
+    const unsigned rHalom = hasR ? mapa_u32(smem_u32(halom), r + 1) : 0u, lHalom = hasL ? mapa_u32(smem_u32(halom), r - 1) : 0u;
+    const unsigned rBars = hasR ? mapa_u32(smem_u32(bars), r + 1) : 0u, lBars = hasL ? mapa_u32(smem_u32(bars), r - 1) : 0u;
+    const unsigned haloBytes = Dp * 2 + 4;          // one pixel's path costs + its packed minimum
     const int iters = (M + NG - 1) / NG;
     const int Mmax = a.Mmax, W1 = a.W1;
     const int rowElems = W1 * Dp;
@@ -711,22 +763,29 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
     uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
     uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
     uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
-    const bool haloWarp = __any_sync(FULL, (g == 0 && haloL != nullptr) || (g == (M - 1) % NG && haloR != nullptr)) != 0;
     if (!PAD) {
         // "No predecessor" is the state (L = 0, m = 0).  Zero every slot once (first row) and both halos (the
         // frame's left / right border never receives a neighbour's write), so the row loop needs no reset tests.
-        const int nwords = (3 * Mmax * Dp + 4 * Dp) / 2 + 3 * Mmax + 4;     // L, halo (u16 pairs), m, halom
+        const int nwords = (3 * Mmax * Dp + 6 * Dp) / 2 + 3 * Mmax + 6;     // L, halo (u16 pairs), m, halom
         unsigned* wz = reinterpret_cast<unsigned*>(smem_raw);
         for (int i = threadIdx.x; i < nwords; i += blockDim.x) wz[i] = 0u;
     }
-    cluster.sync();     // every CTA of the cluster is resident (and initialised) before any remote access
-
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 6; ++i) mbar_init(smem_u32(bars + i), 1);
+        // arm the first phase of every halo that will be received: slot p, direction d = bars[p*2 + d]
+        for (int pp = 0; pp < 3; ++pp) {
+            if (hasL) mbar_expect_tx(smem_u32(bars + pp * 2 + 0), haloBytes);
+            if (hasR) mbar_expect_tx(smem_u32(bars + pp * 2 + 1), haloBytes);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();     // every CTA of the cluster is resident, zeroed and armed before any remote access
     const int lxFirst = min(g, M - 1);
     uint4 CnA = ld128(cbase + lxFirst * Dp), CnB = ld128(cbase + lxFirst * Dp + OB);
     uint4 SnA = ld128(sbase + lxFirst * Dp), SnB = ld128(sbase + lxFirst * Dp + OB);
     int ymod = 0, rowOff = 0;
     for (int yi = 0; yi < a.H; ++yi) {
-        const int par = yi & 1;
+        const int par = yi % 3, parNext = (yi + 1) % 3;      // halo slot read in this row / filled for the next row
         const bool firstRow = yi == 0;
         for (int it = 0; it < iters; ++it) {
             int lx = g + it * NG;
@@ -765,17 +824,26 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
                 uint16_t* sl = L0b + s1 * Dp;
                 const bool fromHalo = lx == 0;
                 const int oa = offA(s1), ob = OB - oa;
+                if (active && fromHalo && hasL && yi > 0) {
+                    // halo slot `par` was filled by the left CTA during its row yi-1: use n of this slot
+                    const int n = (yi - 1) / 3;
+                    mbar_wait(smem_u32(bars + par * 2 + 0), n & 1);
+                }
                 const uint16_t* src = fromHalo ? halo + (par * 2 + 0) * Dp + q * 8 : sl;
                 ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 0] : mb[s1];
+                if (active && fromHalo && hasL && yi > 0 && q == 0 && yi + 3 < a.H)
+                    mbar_expect_tx(smem_u32(bars + par * 2 + 0), haloBytes);                                // arm the next use
                 if (PAD && (firstRow || x == 0)) reset_state2<PAD>(A, B, mm, padA, padB);
                 sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
                 if (active) {
                     st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
                     if (q == 0) mb[s1] = mm;
-                    if (lx == M - 1 && haloR) {
-                        uint16_t* h = haloR + ((par ^ 1) * 2 + 0) * Dp + q * 8;
-                        st128(h, make_uint4(A[0], A[1], A[2], A[3])); st128(h + OB, make_uint4(B[0], B[1], B[2], B[3]));
-                        if (q == 0) halomR[(par ^ 1) * 2 + 0] = mm;
+                    if (lx == M - 1 && hasR && yi + 1 < a.H) {
+                        const int hs = parNext * 2 + 0;
+                        const unsigned h = rHalo + (hs * Dp + q * 8) * 2, rb = rBars + hs * 8;
+                        st_async_v4(h, make_uint4(A[0], A[1], A[2], A[3]), rb);
+                        st_async_v4(h + OB * 2, make_uint4(B[0], B[1], B[2], B[3]), rb);
+                        if (q == 0) st_async_b32(rHalom + hs * 4, mm, rb);
                     }
                 }
                 sat_acc(ScA, A); sat_acc(ScB, B);
@@ -786,17 +854,25 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
                 uint16_t* sl = L2b + s3 * Dp;
                 const bool fromHalo = lx == M - 1;
                 const int oa = offA(s3), ob = OB - oa;
+                if (active && fromHalo && hasR && yi > 0) {
+                    const int n = (yi - 1) / 3;
+                    mbar_wait(smem_u32(bars + par * 2 + 1), n & 1);
+                }
                 const uint16_t* src = fromHalo ? halo + (par * 2 + 1) * Dp + q * 8 : sl;
                 ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 1] : mb[2 * Mmax + s3];
+                if (active && fromHalo && hasR && yi > 0 && q == 0 && yi + 3 < a.H)
+                    mbar_expect_tx(smem_u32(bars + par * 2 + 1), haloBytes);
                 if (PAD && (firstRow || x == W1 - 1)) reset_state2<PAD>(A, B, mm, padA, padB);
                 sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
                 if (active) {
                     st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
                     if (q == 0) mb[2 * Mmax + s3] = mm;
-                    if (lx == 0 && haloL) {
-                        uint16_t* h = haloL + ((par ^ 1) * 2 + 1) * Dp + q * 8;
-                        st128(h, make_uint4(A[0], A[1], A[2], A[3])); st128(h + OB, make_uint4(B[0], B[1], B[2], B[3]));
-                        if (q == 0) halomL[(par ^ 1) * 2 + 1] = mm;
+                    if (lx == 0 && hasL && yi + 1 < a.H) {
+                        const int hs = parNext * 2 + 1;
+                        const unsigned h = lHalo + (hs * Dp + q * 8) * 2, lb = lBars + hs * 8;
+                        st_async_v4(h, make_uint4(A[0], A[1], A[2], A[3]), lb);
+                        st_async_v4(h + OB * 2, make_uint4(B[0], B[1], B[2], B[3]), lb);
+                        if (q == 0) st_async_b32(lHalom + hs * 4, mm, lb);
                     }
                 }
                 sat_acc(ScA, A); sat_acc(ScB, B);
@@ -805,10 +881,9 @@ __global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
         }
         if (++ymod == M) ymod = 0;
         rowOff += rowStep;
-        __syncthreads();
-        cluster_arrive(haloWarp);
-        cluster_wait();
+        __syncthreads();        // the row's slot updates are visible CTA-wide; neighbours are paced by the mbarriers
     }
+    cluster.sync();             // no CTA may exit while a neighbour could still address its shared memory
 }
 
 // K3c + K4: right-to-left path r=(+1,0) fused with winner-take-all, uniqueness, sub-pixel interpolation,
@@ -956,7 +1031,7 @@ inline int td2_threads(int Mmax, int G2) { return (Mmax * G2 >= 1024) ? 512 : 25
 
 inline size_t td_smem_bytes(int Mmax, int Dp)
 {
-    return (size_t)3 * Mmax * Dp * 2 + (size_t)4 * Dp * 2 + (size_t)3 * Mmax * 4 + 4 * 4 + 16;
+    return td_bar_offset(Mmax, Dp) + 6 * 8;
 }
 
 template <int G, bool PAD>
