@@ -1027,7 +1027,27 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
 }
 
 // threads per CTA of the 16-disparity sweep: 512 when the strip gives every lane group >= 2 pixels per row
-inline int td2_threads(int Mmax, int G2) { return (Mmax * G2 >= 1024) ? 512 : 256; }
+inline int td2_threads(int Mmax, int G2)
+{
+    // The row barrier waits for the lane groups with the most pixels, so pick the CTA size (<= 512 threads,
+    // whole warps) whose groups all get (almost) the same number k of pixels: largest size with >= 93 % of the
+    // group-iterations doing useful work; e.g. 344 columns x 4 lanes -> 480 threads (120 groups x 3 = 360 slots).
+    int best = (Mmax * G2 >= 1024) ? 512 : 256;
+    double bestEff = 0.0;
+    {
+        const int groups = best / G2, k = (Mmax + groups - 1) / groups;
+        bestEff = (double)Mmax / ((double)groups * k);
+    }
+    if (bestEff >= 0.93) return best;
+    for (int k = 1; k <= 16; ++k) {
+        const int groups = (Mmax + k - 1) / k;
+        int threads = (groups * G2 + 31) / 32 * 32;
+        if (threads > 512 || threads < 128) continue;
+        const double eff = (double)Mmax / ((double)(threads / G2) * k);
+        if (eff >= 0.93) return threads;          // smallest k = most threads first
+    }
+    return best;
+}
 
 inline size_t td_smem_bytes(int Mmax, int Dp)
 {
