@@ -331,3 +331,20 @@ def test_worst_case_cost_kernel_footprint(oracle):
         e.set_sgbm_params(**gpu_params(p))
         e.compute(l, r, api.STAGE_SGBM)
         check("d256 cap97 bs11", e.download(1)["disp"][0], oracle.sgbm(l, r, p))
+
+
+def test_cpp_frame_loop_demo(tmp_path):
+    """examples/mean_plain_demo.cpp: the reference's application skeleton (worker std::thread + condition variable,
+    trgt/mean_plain.cpp:62-82, trgt/demo.cpp:215-276) running on the engine with a synthetic frame source."""
+    import subprocess
+    root = os.path.dirname(cases.GOLDEN_DIR.rstrip("/").rsplit("/", 1)[0])
+    libdir = os.path.join(root, "mvstereovision3_b200")
+    exe = str(tmp_path / "mean_plain_demo")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-pthread", "-Wall", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "mean_plain_demo.cpp"), "-L" + libdir, "-lmvsv",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.check_output([exe, "--frames", "30"], timeout=120).decode()
+    assert "Disparity Framerate:" in out and "Detection Framerate:" in out, out
+    first = out.splitlines()[0].split()
+    assert first[0] == "frames" and int(first[1]) >= 30 and first[3] == "752x479"
+    assert int(first[first.index("map") + 7]) > 100000        # most of the last map is valid
