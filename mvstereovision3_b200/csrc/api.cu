@@ -55,7 +55,7 @@ int alloc_images(mvsv_ctx* c)
     const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
     for (int i = 0; i < 2; ++i) {
         MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
-        MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg));
+        MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg + 64));      // the BM column-sum kernel reads whole aligned words
     }
     MVSV_CK(c, cudaMalloc(&c->recL, npx * sizeof(uint2)));
     MVSV_CK(c, cudaMalloc(&c->d2, npx * sizeof(int)));

@@ -54,25 +54,50 @@ __global__ void k_bm_tex_row(const uint16_t* __restrict__ tc, int W, int H, int 
     tex[base + x] = s;
 }
 
-// column sums: thread = (k, x'), marching down the valid rows
-__global__ void k_bm_colsum(const uint8_t* __restrict__ preL, const uint8_t* __restrict__ preR, size_t pitch, int H,
-                            int width1, int D, int Dp, int lofs, int w2, uint16_t* __restrict__ col)
+// column sums: lane (x', q) owns the eight disparity indices k = 8q..8q+7 of column x' and marches down the valid
+// rows with a sliding sum.  The eight right-image bytes start at an arbitrary byte address, so they are cut out of
+// three aligned words with PRMT (the selector is constant per thread); |L - R| is VABSDIFF4 on four bytes at once,
+// widened to packed u16x2 for the running sums; one 128-bit store per row.
+__device__ __forceinline__ void bm_ad8(const uint8_t* __restrict__ rowL, const unsigned* __restrict__ rowR, unsigned sel,
+                                       unsigned (&e)[4])
 {
-    const int k = threadIdx.x % Dp;
-    const int xp = blockIdx.x * (blockDim.x / Dp) + threadIdx.x / Dp;
-    if (xp >= width1 || k >= D) return;
+    const unsigned lb = (unsigned)rowL[0] * 0x01010101u;
+    const unsigned w0 = rowR[0], w1 = rowR[1], w2 = rowR[2];
+    const unsigned dlo = __vabsdiffu4(lb, __byte_perm(w0, w1, sel));
+    const unsigned dhi = __vabsdiffu4(lb, __byte_perm(w1, w2, sel));
+    e[0] = __byte_perm(dlo, 0, 0x4140); e[1] = __byte_perm(dlo, 0, 0x4342);
+    e[2] = __byte_perm(dhi, 0, 0x4140); e[3] = __byte_perm(dhi, 0, 0x4342);
+}
+
+template <int G>
+__global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ preL, const uint8_t* __restrict__ preR,
+                                                   size_t pitch, int H, int width1, int D, int lofs, int w2,
+                                                   uint16_t* __restrict__ col)
+{
+    constexpr int Dp = 8 * G;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xp = gtid / G, q = gtid % G;
+    if (xp >= width1 || q * 8 >= D) return;
     const size_t fo = (size_t)blockIdx.y * H * pitch;
     const uint8_t* pl = preL + fo + xp + lofs;
-    const uint8_t* pr = preR + fo + xp + k;
+    const size_t ra = fo + xp + q * 8;                       // byte address of R[.][x' + 8q]
+    const unsigned* pr = reinterpret_cast<const unsigned*>(preR + (ra & ~(size_t)3));
+    const unsigned sel = 0x3210u + 0x1111u * (unsigned)(ra & 3);
+    const size_t pw = pitch / 4;                             // pitch is a multiple of 64 bytes
     const int bs = 2 * w2 + 1;
-    int s = 0;
-    for (int y = 0; y < bs; ++y) s += abs((int)pl[(size_t)y * pitch] - (int)pr[(size_t)y * pitch]);
-    uint16_t* out = col + ((size_t)blockIdx.y * H * width1 + xp) * Dp + k;
+    unsigned acc[4] = {0, 0, 0, 0}, e[4];
+    for (int y = 0; y < bs; ++y) {
+        bm_ad8(pl + (size_t)y * pitch, pr + (size_t)y * pw, sel, e);
+        acc[0] += e[0]; acc[1] += e[1]; acc[2] += e[2]; acc[3] += e[3];
+    }
+    uint16_t* out = col + ((size_t)blockIdx.y * H * width1 + xp) * Dp + q * 8;
     for (int y = w2; y < H - w2; ++y) {
-        out[(size_t)y * width1 * Dp] = (uint16_t)s;
+        st128(out + (size_t)y * width1 * Dp, make_uint4(acc[0], acc[1], acc[2], acc[3]));
         if (y + 1 < H - w2) {
-            const size_t a = (size_t)(y + 1 + w2) * pitch, b = (size_t)(y - w2) * pitch;
-            s += abs((int)pl[a] - (int)pr[a]) - abs((int)pl[b] - (int)pr[b]);
+            unsigned f[4];
+            bm_ad8(pl + (size_t)(y + 1 + w2) * pitch, pr + (size_t)(y + 1 + w2) * pw, sel, e);
+            bm_ad8(pl + (size_t)(y - w2) * pitch, pr + (size_t)(y - w2) * pw, sel, f);
+            acc[0] += e[0] - f[0]; acc[1] += e[1] - f[1]; acc[2] += e[2] - f[2]; acc[3] += e[3] - f[3];
         }
     }
 }
@@ -195,12 +220,16 @@ void launch_bm(mvsv_ctx* c, int B)
         { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2); }
     }
     {
-        const int tpb = n.Dp >= 128 ? n.Dp : 128;
-        const int xper = tpb / n.Dp;
-        dim3 grd((n.width1 + xper - 1) / xper, B);
+        const long long threads = (long long)n.width1 * n.G;
+        dim3 grd((unsigned)((threads + 127) / 128), B);
         KernelTimer kt(c, KID_BM_COLSUM);
-        k_bm_colsum<<<grd, tpb, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.Dp, n.lofs, n.w2,
-                                                c->bm_col);
+        switch (n.G) {
+            case 2: k_bm_colsum<2><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 4: k_bm_colsum<4><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 8: k_bm_colsum<8><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 16: k_bm_colsum<16><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            default: k_bm_colsum<32><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+        }
     }
     BmArgs a;
     a.col = c->bm_col; a.tex = c->bm_tex2; a.disp = c->disp; a.W = W; a.H = H; a.width1 = n.width1; a.D = n.D; a.Dp = n.Dp;
