@@ -348,3 +348,19 @@ def test_cpp_frame_loop_demo(tmp_path):
     first = out.splitlines()[0].split()
     assert first[0] == "frames" and int(first[1]) >= 30 and first[3] == "752x479"
     assert int(first[first.index("map") + 7]) > 100000        # most of the last map is valid
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("nc", [2, 4])
+def test_fused_sweep_degenerate_strips(oracle, H, nc):
+    """Halo hand-off corner cases: frames of 1..7 rows (fewer rows than halo slots) and column strips of one or two
+    pixels (a strip's first pixel is also its last), MODE_HH so that both sweeps run."""
+    p = cases.sgbm_params(numDisp=16, blockSize=3, P1=7, P2=40, uniquenessRatio=5, mode=1)
+    W = 16 + 5                                   # W1 = 5 -> strips of 1 or 2 columns at cluster size 4
+    l, r = synth.random_pair(H, W, seed=90 + H)
+    with api.Engine(W, H) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.debug_set_flags(nc << 8)
+        assert e.info.sgbm_td_cluster == nc
+        e.compute(l, r, api.STAGE_SGBM)
+        check("H=%d nc=%d" % (H, nc), e.download(1)["disp"][0], oracle.sgbm(l, r, p))
