@@ -288,7 +288,7 @@ class Engine:
         elif which in (2, 4):
             a = np.empty((batch, H, W), np.int16)
         else:
-            pitch = (W + 63) // 64 * 64
+            pitch = (W + 15) // 16 * 16
             a = np.empty((batch, H, pitch), np.uint8)
         n = self._ck(self._lib.mvsv_debug_read(self._ctx, which, a.ctypes.data, a.nbytes))
         assert n == a.nbytes, (n, a.nbytes)

@@ -51,7 +51,9 @@ void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
 int alloc_images(mvsv_ctx* c)
 {
     free_images(c);
-    c->pitch = round_up((size_t)c->W, 64);
+    // 16-byte aligned rows; when the width already is (752, 1920, 3840, ...) a batch is one contiguous block and
+    // host <-> device transfers are single linear copies instead of strided 2-D copies of many short rows
+    c->pitch = round_up((size_t)c->W, 16);
     const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
     for (int i = 0; i < 2; ++i) {
         MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
@@ -170,7 +172,9 @@ int upload_images(mvsv_ctx* c, uint8_t* dst, size_t dpitch, const uint8_t* src, 
                   int h, int batch, bool device_src)
 {
     const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (frame_stride == sstride * (size_t)h) {
+    if (sstride == (size_t)w && dpitch == (size_t)w && (batch == 1 || frame_stride == (size_t)w * h)) {
+        MVSV_CK(c, cudaMemcpyAsync(dst, src, (size_t)w * h * batch, kind, c->stream));
+    } else if (frame_stride == sstride * (size_t)h) {
         MVSV_CK(c, cudaMemcpy2DAsync(dst, dpitch, src, sstride, (size_t)w, (size_t)h * batch, kind, c->stream));
     } else {
         for (int b = 0; b < batch; ++b)
@@ -364,7 +368,7 @@ int mvsv_upload_rectify_maps(mvsv_ctx* c, int cam, const float* mapx, const floa
     rc = resize_rectified(c, roi_w, roi_h);
     if (rc) return rc;
     if (!c->raw[0]) {
-        c->raw_pitch = round_up((size_t)c->fw, 64);
+        c->raw_pitch = round_up((size_t)c->fw, 16);
         for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
     }
     dfree(c->map_xy[cam]);
@@ -446,8 +450,11 @@ int mvsv_download(mvsv_ctx* c, int16_t* disp, size_t dstride, uint8_t* rectL, ui
     if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
     if (disp) {
         if (dstride < (size_t)c->W * 2) return fail(c, MVSV_ERR_INVALID, "disparity stride too small");
-        MVSV_CK(c, cudaMemcpy2DAsync(disp, dstride, c->disp, (size_t)c->W * 2, (size_t)c->W * 2, (size_t)c->H * B,
-                                     cudaMemcpyDeviceToHost, c->stream));
+        if (dstride == (size_t)c->W * 2)
+            MVSV_CK(c, cudaMemcpyAsync(disp, c->disp, (size_t)c->W * 2 * c->H * B, cudaMemcpyDeviceToHost, c->stream));
+        else
+            MVSV_CK(c, cudaMemcpy2DAsync(disp, dstride, c->disp, (size_t)c->W * 2, (size_t)c->W * 2, (size_t)c->H * B,
+                                         cudaMemcpyDeviceToHost, c->stream));
     }
     uint8_t* r[2] = {rectL, rectR};
     for (int i = 0; i < 2; ++i)

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ p
     const size_t ra = fo + xp + q * 8;                       // byte address of R[.][x' + 8q]
     const unsigned* pr = reinterpret_cast<const unsigned*>(preR + (ra & ~(size_t)3));
     const unsigned sel = 0x3210u + 0x1111u * (unsigned)(ra & 3);
-    const size_t pw = pitch / 4;                             // pitch is a multiple of 64 bytes
+    const size_t pw = pitch / 4;                             // pitch is a multiple of 16 bytes
     const int bs = 2 * w2 + 1;
     unsigned acc[4] = {0, 0, 0, 0}, e[4];
     for (int y = 0; y < bs; ++y) {
