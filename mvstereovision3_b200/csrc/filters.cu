@@ -72,7 +72,7 @@ __global__ void k_median3(const int16_t* __restrict__ in, int16_t* __restrict__ 
 //   1. rows:    every pixel gets the index of the first pixel of its horizontal run (warp ballot scan)
 //   2. vmerge:  lock-free union (atomicMin) of vertically connected runs, skipping links the left
 //               neighbour already established
-//   3. flatten: label := root; the last pixel of each run adds the run length to the root's size
+//   3. flatten: run starts := root; the last pixel of each run adds the run length to the root's size
 //   4. apply:   components with size <= maxSize are set to newVal
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool conn(int a, int b, int newVal, int maxDiff)
@@ -139,20 +139,10 @@ __global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ 
     ccl_unite(label, label[i], label[u]);
 }
 
-// phase 1: only the run starts (the union-find tree nodes) chase their root and point straight at it
-__global__ void k_ccl_flatten_starts(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int newVal,
-                                     int maxDiff)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
-    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
-    const int l = label[i];
-    if (l < 0) return;
-    const bool runStart = (x == 0) || !conn(img[i], img[i - 1], newVal, maxDiff);
-    if (runStart && l != (int)i) label[i] = ccl_find(label, l);     // monotone: always an ancestor, races are benign
-}
-
-// phase 2: every pixel is now at most two hops from its root; the last pixel of each run adds the run length
+// One pass after all unions: run starts (the union-find tree nodes) are pointed straight at their root, so that the
+// apply pass finds any pixel's root in at most two hops, and the last pixel of each run adds the run length to the
+// root's size.  Compressing links while other threads still walk them is benign: a link only ever moves to an
+// ancestor (monotone decreasing indices).
 __global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ sizes, int W,
                               int H, int newVal, int maxDiff)
 {
@@ -165,11 +155,12 @@ __global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__
     const int v = img[i];
     const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
     const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
-    if (!runEnd) return;
-    // label of a run start = tree link (root after phase 1, or itself); label of other pixels = their run start
+    if (!runStart && !runEnd) return;
+    // label of a run start = tree link; label of the other pixels = their run start
     const int start = runStart ? (int)i : l;
     const int root = ccl_find(label, start);
-    atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
+    if (runStart && l != root) label[i] = root;
+    if (runEnd) atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
 }
 
 __global__ void k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const int* __restrict__ label,
@@ -179,7 +170,7 @@ __global__ void k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict
     if (i >= n) return;
     const int l = label[i];
     if (l < 0) { out[i] = (int16_t)newVal; return; }
-    const int root = ccl_find(label, l);          // <= 2 hops after k_ccl_flatten_starts
+    const int root = ccl_find(label, l);          // <= 2 hops after k_ccl_flatten
     out[i] = (sizes[root] <= maxSize) ? (int16_t)newVal : img[i];
 }
 
@@ -308,7 +299,6 @@ void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int ne
         KernelTimer kt(c, KID_CCL_VMERGE);
         k_ccl_vmerge<<<grdv, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
     }
-    { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten_starts<<<grd, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff); }
     { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff); }
     { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, out, c->labels, c->sizes, n, newVal, maxSize); }
 }
