@@ -60,6 +60,31 @@ def measured_traffic_per_cell():
         return {}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and allocate its pinned host buffers) on the CPUs of the NUMA node its GPU hangs
+    off, so that host<->device copies of different ranks do not cross sockets.  Returns a short description."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa node %d (%d cpus)" % (node, len(allowed))
+    except Exception as e:          # no sysfs, container restrictions, ...
+        return "not bound (%s)" % type(e).__name__
+
+
 def w1_of(W, p):
     maxD = p["minDisp"] + p["numDisp"]
     return (W + min(p["minDisp"], 0)) - max(maxD, 0)
@@ -243,6 +268,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process, not bound"
 
     cfg = CFG
     p, H, W, B = cfg["params"], cfg["H"], cfg["W"], args.batch
@@ -391,7 +417,7 @@ def main():
             "gdisp_evals_per_s": W * H * p["numDisp"] * fps / 1e9,
             "evaluated_gcells_per_s": cells_per_frame * fps / 1e9,
             "config": {"workload": cfg["name"], "batch_per_gpu": B, "frames_per_step": B * world,
-                       "sharding": "frame i -> rank i mod N, no collective",
+                       "sharding": "frame i -> rank i mod N, no collective", "host_binding_rank0": numa,
                        "l2": "working set per step (3 int16 volumes x %d frames = %.1f GB) exceeds the 126 MB L2"
                              % (B, 3 * 2 * cells_per_frame * B / 1e9)},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * H * W,
