@@ -364,3 +364,23 @@ def test_fused_sweep_degenerate_strips(oracle, H, nc):
         assert e.info.sgbm_td_cluster == nc
         e.compute(l, r, api.STAGE_SGBM)
         check("H=%d nc=%d" % (H, nc), e.download(1)["disp"][0], oracle.sgbm(l, r, p))
+
+
+@pytest.mark.parametrize("nc", [1, 2, 4, 8])
+def test_halo_handoff_soak(oracle, nc):
+    """Determinism soak of the st.async + mbarrier halo hand-off: 100 x 24 small MODE_HH frames (two sweeps each)
+    at every cluster size, each result identical to the oracle."""
+    p = cases.sgbm_params(minDisp=1, numDisp=32, blockSize=5, P1=20, P2=90, uniquenessRatio=5, disp12MaxDiff=1,
+                          speckleWindowSize=30, speckleRange=2, mode=1)
+    H, W, B = 37, 171, 24
+    ls, rs = zip(*[synth.random_pair(H, W, seed=s) for s in range(B)])
+    L, R = np.stack(ls), np.stack(rs)
+    want = np.stack([oracle.sgbm(ls[b], rs[b], p) for b in range(B)])
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.debug_set_flags(nc << 8)
+        assert e.info.sgbm_td_cluster == nc
+        for it in range(100):
+            e.compute(L, R, api.STAGE_SGBM)
+            got = e.download(B)["disp"]
+            assert np.array_equal(got, want), "cluster %d, iteration %d: %d pixels differ" % (nc, it, int((got != want).sum()))
