@@ -83,6 +83,20 @@ int mvsv_set_bm_params(mvsv_ctx* ctx, const mvsv_bm_params* p);
  * to OpenCV's fixed-point (CV_16SC2 + 5-bit fractions) form on the device.  stride is in bytes. */
 int mvsv_upload_rectify_maps(mvsv_ctx* ctx, int cam, const float* mapx, const float* mapy, size_t stride_bytes,
                              int roi_x, int roi_y, int roi_w, int roi_h);
+/* The same state built on the device from the calibration itself: replaces the call
+ * cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1, map1, map2) of Stereosystem::initRectification
+ * (src/Stereosystem.cpp:214-217) together with the upload above.  K: 3x3 camera matrix (intrinsic.yml, halved for
+ * binning as src/Stereosystem.cpp:203-208 does), dist: n_dist = 0, 4 or 5 coefficients k1 k2 p1 p2 [k3]
+ * (mDistCoeffs), R: 3x3 rectifying rotation and P: 3x4 projection from cv::stereoRectify (mR0/mR1, mP0/mP1),
+ * all row-major doubles as the cv::Mat's hold them.  The fixed-point maps equal the ones OpenCV derives from its
+ * float maps (cv2 4.13: identical for the reference's three calibrations, tests/test_rectify_maps.py). */
+int mvsv_set_rectification(mvsv_ctx* ctx, int cam, const double K[9], const double* dist, int n_dist,
+                           const double R[9], const double P[12], int roi_x, int roi_y, int roi_w, int roi_h);
+/* Stereosystem::getRectifiedImagepair(sip, factor) (src/Stereosystem.cpp:279-315): after remap + crop the pair is
+ * scaled with cv::resize(roi, dst, cv::Size(0,0), factor, factor) (INTER_LINEAR, which OpenCV replaces by its 2x2
+ * area average at factor 0.5 -- the value trgt/test.cpp:213 passes).  Applies to MVSV_STAGE_RECTIFY computes; width
+ * and height of mvsv_get_info become cvRound(roi * factor).  factor <= 0 or == 1 switches it off. */
+int mvsv_set_resize(mvsv_ctx* ctx, double factor);
 /* Stereosystem::resetRectification (src/Stereosystem.cpp:317-320): inputs are taken as already rectified. */
 int mvsv_reset_rectification(mvsv_ctx* ctx);
 
@@ -139,7 +153,8 @@ int mvsv_host_free(void* p);
 /* Test hooks: read an internal device buffer of the last compute into host memory.
  * which: 0 = cost volume C, 1 = aggregated S (before the final right-to-left pass), 2 = raw disparity
  * (after LR check, before median), 3 = vertical-sum volume, 4 = disparity after median (before speckle),
- * 5 = BM prefiltered left, 6 = BM prefiltered right.  Returns bytes written or a negative error. */
+ * 5 = BM prefiltered left, 6 = BM prefiltered right, 7 / 8 = fixed-point rectification map of camera 0 / 1
+ * (roi_h x roi_w int32 pairs: x*32, y*32 rounded).  Returns bytes written or a negative error. */
 /* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
  * bits 8..15: force the cluster size of the fused sweep (1,2,4,8,16; 0xff = force the independent passes). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);

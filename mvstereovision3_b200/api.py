@@ -16,7 +16,7 @@ STAGE_RECTIFY, STAGE_SGBM, STAGE_BM, STAGE_XYZ, STAGE_MEANS = 1, 2, 4, 8, 16
 # every symbol include/mvsv.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = (
     "mvsv_init", "mvsv_destroy", "mvsv_last_error", "mvsv_set_sgbm_params", "mvsv_set_bm_params",
-    "mvsv_upload_rectify_maps", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
+    "mvsv_upload_rectify_maps", "mvsv_set_rectification", "mvsv_set_resize", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
     "mvsv_compute_device", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
     "mvsv_host_alloc", "mvsv_host_free", "mvsv_debug_set_flags", "mvsv_debug_read",
     "mvsv_download_minmax", "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
@@ -67,6 +67,8 @@ def load_library():
     lib.mvsv_set_sgbm_params.argtypes = [vp, C.POINTER(SgbmParams)]
     lib.mvsv_set_bm_params.argtypes = [vp, C.POINTER(BmParams)]
     lib.mvsv_upload_rectify_maps.argtypes = [vp, ci, vp, vp, sz, ci, ci, ci, ci]
+    lib.mvsv_set_rectification.argtypes = [vp, ci, vp, vp, ci, vp, vp, ci, ci, ci, ci]
+    lib.mvsv_set_resize.argtypes = [vp, C.c_double]
     lib.mvsv_reset_rectification.argtypes = [vp]
     lib.mvsv_set_Q.argtypes = [vp, vp]
     lib.mvsv_set_mean_rois.argtypes = [vp, vp, ci]
@@ -189,6 +191,26 @@ class Engine:
         mapy = np.ascontiguousarray(mapy, np.float32)
         self._ck(self._lib.mvsv_upload_rectify_maps(self._ctx, cam, mapx.ctypes.data, mapy.ctypes.data,
                                                     mapx.strides[0], *[int(v) for v in roi]))
+
+    def set_rectification(self, cam, K, dist, R, P, roi):
+        """cv::initUndistortRectifyMap on the device (reference src/Stereosystem.cpp:214-217) + mDisplayROI."""
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel()) if dist is not None else np.zeros(0)
+        R = np.ascontiguousarray(R, np.float64).reshape(9)
+        P = np.ascontiguousarray(P, np.float64).reshape(12)
+        self._ck(self._lib.mvsv_set_rectification(self._ctx, cam, K.ctypes.data, d.ctypes.data if d.size else None,
+                                                  int(d.size), R.ctypes.data, P.ctypes.data, *[int(v) for v in roi]))
+
+    def read_rectify_map(self, cam, roi):
+        """Fixed-point map of one camera as the device holds it: int32 [roi_h, roi_w, 2] = rint(map * 32)."""
+        a = np.empty((int(roi[3]), int(roi[2]), 2), np.int32)
+        n = self._ck(self._lib.mvsv_debug_read(self._ctx, 7 + cam, a.ctypes.data, a.nbytes))
+        assert n == a.nbytes, (n, a.nbytes)
+        return a
+
+    def set_resize(self, factor):
+        """cv::resize(.., factor, factor) after remap + crop (reference src/Stereosystem.cpp:279-315); 0 = off."""
+        self._ck(self._lib.mvsv_set_resize(self._ctx, float(factor)))
 
     def reset_rectification(self):
         self._ck(self._lib.mvsv_reset_rectification(self._ctx))

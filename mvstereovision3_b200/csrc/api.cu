@@ -1,5 +1,6 @@
 // C-ABI glue of libmvsv.so (include/mvsv.h): context, device buffers, parameter normalisation, stage sequencing.
 #include "mvsv_internal.h"
+#include <cmath>
 
 #include <algorithm>
 #include <cstdio>
@@ -202,8 +203,10 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
         if (rc) return rc;
         rc = upload_images(c, c->raw[1], c->raw_pitch, right, rstride, frame_stride, c->fw, c->fh, batch, device_src);
         if (rc) return rc;
-        launch_remap(c, 0, batch);
-        launch_remap(c, 1, batch);
+        for (int cam = 0; cam < 2; ++cam) {
+            launch_remap(c, cam, batch);
+            if (c->resize_factor > 0.0) launch_resize(c, cam, batch);
+        }
     } else {
         if (lstride < (size_t)c->W || rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "stride smaller than image width");
         rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, c->W, c->H, batch, device_src);
@@ -286,7 +289,7 @@ void mvsv_destroy(mvsv_ctx* c)
     free_images(c);
     free_sgbm_volumes(c);
     free_bm_volumes(c);
-    for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); }
+    for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); dfree(c->crop[i]); }
     dfree(c->rois);
     for (auto& b : c->brackets) { cudaEventDestroy(b.a); cudaEventDestroy(b.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
@@ -351,28 +354,61 @@ static int resize_rectified(mvsv_ctx* c, int W, int H)
     return MVSV_OK;
 }
 
+// size of the images the matcher sees: the frame, the display ROI once maps are installed, the resized ROI when
+// mvsv_set_resize is active; (re)allocates everything that depends on it
+static int apply_geometry(mvsv_ctx* c)
+{
+    const bool maps = c->has_maps[0] || c->has_maps[1] || c->map_xy[0] || c->map_xy[1];
+    int W = maps ? c->roi[2] : c->fw, H = maps ? c->roi[3] : c->fh;
+    const bool resized = maps && c->resize_factor > 0.0;
+    if (resized) {
+        // cv::resize: dsize = Size(saturate_cast<int>(w*fx), saturate_cast<int>(h*fy)), round half to even
+        W = (int)lrint((double)W * c->resize_factor);
+        H = (int)lrint((double)H * c->resize_factor);
+        if (W < 2 || H < 1 || W > 16384 || H > 16384) return fail(c, MVSV_ERR_INVALID, "resized image out of range");
+    }
+    int rc = resize_rectified(c, W, H);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) dfree(c->crop[i]);
+    if (resized) {
+        c->crop_pitch = round_up((size_t)c->roi[2], 16);
+        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->crop[i], (size_t)c->maxB * c->roi[3] * c->crop_pitch));
+    }
+    return MVSV_OK;
+}
+
+// shared by the two ways of installing a camera's maps: checks the display ROI, sizes the rectified images and
+// the raw-frame staging, allocates the fixed-point map
+static int prepare_maps(mvsv_ctx* c, int cam, int roi_x, int roi_y, int roi_w, int roi_h)
+{
+    if (roi_x < 0 || roi_y < 0 || roi_w < 2 || roi_h < 1 || roi_x + roi_w > c->fw || roi_y + roi_h > c->fh)
+        return fail(c, MVSV_ERR_INVALID, "display ROI outside the frame");
+    const int other = 1 - cam;
+    if (c->has_maps[other] && (c->roi[0] != roi_x || c->roi[1] != roi_y || c->roi[2] != roi_w || c->roi[3] != roi_h))
+        return fail(c, MVSV_ERR_INVALID, "both cameras must share one display ROI (mDisplayROI)");
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->roi[0] = roi_x; c->roi[1] = roi_y; c->roi[2] = roi_w; c->roi[3] = roi_h;
+    c->has_maps[cam] = false;
+    dfree(c->map_xy[cam]);
+    MVSV_CK(c, cudaMalloc(&c->map_xy[cam], (size_t)roi_w * roi_h * sizeof(int2)));
+    int rc = apply_geometry(c);
+    if (rc) return rc;
+    if (!c->raw[0]) {
+        c->raw_pitch = round_up((size_t)c->fw, 16);
+        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
+    }
+    return MVSV_OK;
+}
+
 int mvsv_upload_rectify_maps(mvsv_ctx* c, int cam, const float* mapx, const float* mapy, size_t stride_bytes, int roi_x,
                              int roi_y, int roi_w, int roi_h)
 {
     if (!c || !mapx || !mapy || cam < 0 || cam > 1) return MVSV_ERR_INVALID;
     int rc = bind(c);
     if (rc) return rc;
-    if (roi_x < 0 || roi_y < 0 || roi_w < 2 || roi_h < 1 || roi_x + roi_w > c->fw || roi_y + roi_h > c->fh)
-        return fail(c, MVSV_ERR_INVALID, "display ROI outside the frame");
     if (stride_bytes < (size_t)c->fw * sizeof(float) || stride_bytes % sizeof(float)) return fail(c, MVSV_ERR_INVALID, "bad map stride");
-    const int other = 1 - cam;
-    if (c->has_maps[other] && (c->roi[0] != roi_x || c->roi[1] != roi_y || c->roi[2] != roi_w || c->roi[3] != roi_h))
-        return fail(c, MVSV_ERR_INVALID, "both cameras must share one display ROI (mDisplayROI)");
-    MVSV_CK(c, cudaStreamSynchronize(c->stream));
-    c->roi[0] = roi_x; c->roi[1] = roi_y; c->roi[2] = roi_w; c->roi[3] = roi_h;
-    rc = resize_rectified(c, roi_w, roi_h);
+    rc = prepare_maps(c, cam, roi_x, roi_y, roi_w, roi_h);
     if (rc) return rc;
-    if (!c->raw[0]) {
-        c->raw_pitch = round_up((size_t)c->fw, 16);
-        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
-    }
-    dfree(c->map_xy[cam]);
-    MVSV_CK(c, cudaMalloc(&c->map_xy[cam], (size_t)roi_w * roi_h * sizeof(int2)));
     float *dx = nullptr, *dy = nullptr;
     const size_t mbytes = (size_t)c->fw * c->fh * sizeof(float);
     MVSV_CK(c, cudaMalloc(&dx, mbytes));
@@ -391,13 +427,67 @@ int mvsv_upload_rectify_maps(mvsv_ctx* c, int cam, const float* mapx, const floa
     return MVSV_OK;
 }
 
+int mvsv_set_rectification(mvsv_ctx* c, int cam, const double K[9], const double* dist, int n_dist, const double R[9],
+                           const double P[12], int roi_x, int roi_y, int roi_w, int roi_h)
+{
+    if (!c || !K || !R || !P || cam < 0 || cam > 1 || n_dist < 0 || (n_dist > 0 && !dist)) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (n_dist != 0 && n_dist != 4 && n_dist != 5)
+        return fail(c, MVSV_ERR_UNSUPPORTED, "distortion model: 0, 4 or 5 coefficients (k1 k2 p1 p2 [k3])");
+    // iR = (P[:, :3] * R)^-1, the 3x3 closed form (cofactors / determinant)
+    double A[9];
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) {
+            double acc = 0;
+            for (int m = 0; m < 3; ++m) acc += P[r * 4 + m] * R[m * 3 + k];
+            A[r * 3 + k] = acc;
+        }
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[3] * A[8] - A[5] * A[6], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 - A[1] * c01 + A[2] * c02;
+    if (!(det != 0.0) || !std::isfinite(det)) return fail(c, MVSV_ERR_INVALID, "P[:, :3]*R is singular");
+    const double d = 1.0 / det;
+    RectifyCoef q;
+    q.iR[0] = c00 * d;                         q.iR[1] = (A[2] * A[7] - A[1] * A[8]) * d;  q.iR[2] = (A[1] * A[5] - A[2] * A[4]) * d;
+    q.iR[3] = (A[5] * A[6] - A[3] * A[8]) * d;  q.iR[4] = (A[0] * A[8] - A[2] * A[6]) * d;  q.iR[5] = (A[2] * A[3] - A[0] * A[5]) * d;
+    q.iR[6] = c02 * d;                         q.iR[7] = (A[1] * A[6] - A[0] * A[7]) * d;  q.iR[8] = (A[0] * A[4] - A[1] * A[3]) * d;
+    q.k1 = n_dist > 0 ? dist[0] : 0; q.k2 = n_dist > 1 ? dist[1] : 0; q.p1 = n_dist > 2 ? dist[2] : 0;
+    q.p2 = n_dist > 3 ? dist[3] : 0; q.k3 = n_dist > 4 ? dist[4] : 0;
+    q.fx = K[0]; q.fy = K[4]; q.cx = K[2]; q.cy = K[5];
+    rc = prepare_maps(c, cam, roi_x, roi_y, roi_w, roi_h);
+    if (rc) return rc;
+    launch_rectify_maps(c, cam, q);
+    MVSV_CK(c, cudaGetLastError());
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    c->has_maps[cam] = true;
+    return MVSV_OK;
+}
+
 int mvsv_reset_rectification(mvsv_ctx* c)
 {
     if (!c) return MVSV_ERR_INVALID;
     int rc = bind(c);
     if (rc) return rc;
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
     c->has_maps[0] = c->has_maps[1] = false;
-    return resize_rectified(c, c->fw, c->fh);
+    for (int i = 0; i < 2; ++i) dfree(c->map_xy[i]);
+    return apply_geometry(c);
+}
+
+int mvsv_set_resize(mvsv_ctx* c, double factor)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (!(factor == factor) || factor > 8.0) return fail(c, MVSV_ERR_INVALID, "resize factor must be in (0, 8]");
+    if (factor <= 0.0 || factor == 1.0) factor = 0.0;       // off: cv::resize by 1 is the identity
+    if (factor > 0.0 && factor < 1.0 / 64) return fail(c, MVSV_ERR_INVALID, "resize factor must be in (0, 8]");
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    const double old = c->resize_factor;
+    c->resize_factor = factor;
+    rc = apply_geometry(c);
+    if (rc) { c->resize_factor = old; apply_geometry(c); }
+    return rc;
 }
 
 int mvsv_set_Q(mvsv_ctx* c, const float q[16])
@@ -586,10 +676,20 @@ long long mvsv_debug_read(mvsv_ctx* c, int which, void* host, size_t cap)
     if (!c || !host) return MVSV_ERR_INVALID;
     int rc = bind(c);
     if (rc) return rc;
-    const int B = c->lastB;
-    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
     const void* src = nullptr;
     size_t bytes = 0;
+    if (which == 7 || which == 8) {
+        const int cam = which - 7;
+        if (!c->has_maps[cam]) return fail(c, MVSV_ERR_STATE, "no rectification map for this camera");
+        src = c->map_xy[cam];
+        bytes = (size_t)c->roi[2] * c->roi[3] * sizeof(int2);
+        if (bytes > cap) return fail(c, MVSV_ERR_INVALID, "host buffer too small");
+        MVSV_CK(c, cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        MVSV_CK(c, cudaStreamSynchronize(c->stream));
+        return (long long)bytes;
+    }
+    const int B = c->lastB;
+    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
     const size_t vol = c->has_sgbm && c->sg.W1 > 0 ? (size_t)B * c->H * c->sg.W1 * c->sg.Dp * 2 : 0;
     const size_t img16 = (size_t)B * c->H * c->W * 2;
     switch (which) {

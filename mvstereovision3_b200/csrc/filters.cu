@@ -1,5 +1,7 @@
 // Rectification (K1), 3x3 median (K5), speckle filter (K6), reprojection + ROI means (K8) on sm_100a.
 #include "mvsv_internal.h"
+#include <cfloat>
+#include <cmath>
 
 namespace {
 
@@ -14,6 +16,28 @@ __global__ void k_convert_maps(const float* __restrict__ mx, const float* __rest
     if (x >= rw || y >= rh) return;
     size_t mi = (size_t)(y + ry) * strideElems + (size_t)(x + rx);
     out[(size_t)y * rw + x] = make_int2(__float2int_rn(mx[mi] * 32.0f), __float2int_rn(my[mi] * 32.0f));
+}
+
+// cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1) evaluated straight into the fixed-point map
+// (reference src/Stereosystem.cpp:214-217).  Double precision with explicitly rounded multiplies and adds
+// (no fused multiply-add), the float rounding of the CV_32FC1 map, then the same x32 conversion as above.
+__global__ void k_rectify_maps(RectifyCoef q, int rx, int ry, int rw, int rh, int2* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= rw || y >= rh) return;
+    const double j = (double)(x + rx), i = (double)(y + ry);
+    auto lin = [&](const double* r) { return __dadd_rn(__dadd_rn(__dmul_rn(j, r[0]), __dmul_rn(i, r[1])), r[2]); };
+    const double w = lin(q.iR + 6);
+    const double px = __ddiv_rn(lin(q.iR), w), py = __ddiv_rn(lin(q.iR + 3), w);
+    const double x2 = __dmul_rn(px, px), y2 = __dmul_rn(py, py), r2 = __dadd_rn(x2, y2);
+    const double _2xy = __dmul_rn(__dmul_rn(2.0, px), py);
+    const double kr = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(q.k3, r2), q.k2), r2), q.k1), r2));
+    const double xd = __dadd_rn(__dadd_rn(__dmul_rn(px, kr), __dmul_rn(q.p1, _2xy)),
+                                __dmul_rn(q.p2, __dadd_rn(r2, __dmul_rn(2.0, x2))));
+    const double yd = __dadd_rn(__dadd_rn(__dmul_rn(py, kr), __dmul_rn(q.p1, __dadd_rn(r2, __dmul_rn(2.0, y2)))),
+                                __dmul_rn(q.p2, _2xy));
+    const float u = (float)__dadd_rn(__dmul_rn(q.fx, xd), q.cx), v = (float)__dadd_rn(__dmul_rn(q.fy, yd), q.cy);
+    out[(size_t)y * rw + x] = make_int2(__float2int_rn(u * 32.0f), __float2int_rn(v * 32.0f));
 }
 
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
@@ -41,6 +65,54 @@ __global__ void k_remap(const uint8_t* __restrict__ src, size_t spitch, int fw, 
     const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
     const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 16384) >> 15;
     dst[((size_t)f * H + y) * dpitch + x] = (uint8_t)max(0, min(255, v));
+}
+
+// cv::resize(src, dst, Size(0,0), f, f) for CV_8UC1, default INTER_LINEAR (reference src/Stereosystem.cpp:294-295):
+// 11-bit fixed-point separable bilinear; horizontal taps clamp the coordinate and zero the fraction at the image
+// edge, vertical taps clamp only the row index.  OpenCV switches to its 2x2 area average when the scale is exactly
+// 1/2 (full blocks (a+b+c+d+2)>>2, clipped blocks at an odd edge: float mean rounded to nearest even).
+__global__ void k_resize_linear(const uint8_t* __restrict__ src, size_t spitch, int sw, int sh, uint8_t* __restrict__ dst,
+                                size_t dpitch, int dw, int dh, double scale)
+{
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, f = blockIdx.z;
+    if (dx >= dw) return;
+    float fx = (float)__dadd_rn(__dmul_rn((double)dx + 0.5, scale), -0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= sw - 1) { sx = sw - 1; fx = 0.f; }
+    float fy = (float)__dadd_rn(__dmul_rn((double)dy + 0.5, scale), -0.5);
+    const int sy = (int)floorf(fy);
+    fy -= (float)sy;
+    const int a0 = __float2int_rn((1.f - fx) * 2048.f), a1 = __float2int_rn(fx * 2048.f);
+    const int b0 = __float2int_rn((1.f - fy) * 2048.f), b1 = __float2int_rn(fy * 2048.f);
+    const uint8_t* img = src + (size_t)f * sh * spitch;
+    const uint8_t* r0 = img + (size_t)min(max(sy, 0), sh - 1) * spitch;
+    const uint8_t* r1 = img + (size_t)min(max(sy + 1, 0), sh - 1) * spitch;
+    const int x1 = min(sx + 1, sw - 1);
+    const int s0 = r0[sx] * a0 + r0[x1] * a1, s1 = r1[sx] * a0 + r1[x1] * a1;
+    const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    dst[((size_t)f * dh + dy) * dpitch + dx] = (uint8_t)max(0, min(255, v));
+}
+
+__global__ void k_resize_half(const uint8_t* __restrict__ src, size_t spitch, int sw, int sh, uint8_t* __restrict__ dst,
+                              size_t dpitch, int dw, int dh)
+{
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, f = blockIdx.z;
+    if (dx >= dw) return;
+    const uint8_t* img = src + (size_t)f * sh * spitch;
+    const int x0 = 2 * dx, y0 = 2 * dy;
+    int v;
+    if (x0 + 2 <= sw && y0 + 2 <= sh) {
+        const uint8_t *r0 = img + (size_t)y0 * spitch, *r1 = r0 + spitch;
+        v = (r0[x0] + r0[x0 + 1] + r1[x0] + r1[x0 + 1] + 2) >> 2;
+    } else {
+        int sum = 0, cnt = 0;
+        for (int y = y0; y < min(y0 + 2, sh); ++y)
+            for (int x = x0; x < min(x0 + 2, sw); ++x) { sum += img[(size_t)y * spitch + x]; ++cnt; }
+        v = cnt ? __float2int_rn(__fdiv_rn((float)sum, (float)cnt)) : 0;
+    }
+    dst[((size_t)f * dh + dy) * dpitch + dx] = (uint8_t)v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,12 +343,34 @@ void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* 
                                                c->map_xy[cam]);
 }
 
+void launch_rectify_maps(mvsv_ctx* c, int cam, const RectifyCoef& q)
+{
+    dim3 blk(128), grd((c->roi[2] + 127) / 128, c->roi[3]);
+    KernelTimer kt(c, KID_REMAP);
+    k_rectify_maps<<<grd, blk, 0, c->stream>>>(q, c->roi[0], c->roi[1], c->roi[2], c->roi[3], c->map_xy[cam]);
+}
+
 void launch_remap(mvsv_ctx* c, int cam, int B)
 {
+    const int rw = c->roi[2], rh = c->roi[3];
+    const bool resized = c->resize_factor > 0.0;
+    dim3 blk(128), grd((rw + 127) / 128, rh, B);
+    KernelTimer kt(c, KID_REMAP);
+    k_remap<<<grd, blk, 0, c->stream>>>(c->raw[cam], c->raw_pitch, c->fw, c->fh, c->map_xy[cam],
+                                        resized ? c->crop[cam] : c->rect[cam], resized ? c->crop_pitch : c->pitch, rw, rh);
+}
+
+void launch_resize(mvsv_ctx* c, int cam, int B)
+{
+    const int rw = c->roi[2], rh = c->roi[3];
+    const double scale = 1.0 / c->resize_factor;
+    const long iscale = lrint(scale);
     dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
     KernelTimer kt(c, KID_REMAP);
-    k_remap<<<grd, blk, 0, c->stream>>>(c->raw[cam], c->raw_pitch, c->fw, c->fh, c->map_xy[cam], c->rect[cam], c->pitch,
-                                        c->W, c->H);
+    if (fabs(scale - (double)iscale) < DBL_EPSILON && iscale == 2)
+        k_resize_half<<<grd, blk, 0, c->stream>>>(c->crop[cam], c->crop_pitch, rw, rh, c->rect[cam], c->pitch, c->W, c->H);
+    else
+        k_resize_linear<<<grd, blk, 0, c->stream>>>(c->crop[cam], c->crop_pitch, rw, rh, c->rect[cam], c->pitch, c->W, c->H, scale);
 }
 
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)

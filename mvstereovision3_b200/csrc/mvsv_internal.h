@@ -57,6 +57,11 @@ struct mvsv_ctx {
     int2* map_xy[2] = {nullptr, nullptr};     // (ix, iy) = rint(map*32), saturated int32
     uint8_t* raw[2] = {nullptr, nullptr};     // [B][fh][raw_pitch]
     size_t raw_pitch = 0;
+    // cv::resize(.., factor, factor) after the crop (Stereosystem::getRectifiedImagepair(sip, factor),
+    // reference src/Stereosystem.cpp:279-315); off when resize_factor == 0
+    double resize_factor = 0.0;
+    uint8_t* crop[2] = {nullptr, nullptr};    // [B][roi_h][crop_pitch]: remap output when a resize follows
+    size_t crop_pitch = 0;
 
     uint8_t* rect[2] = {nullptr, nullptr};    // [B][H][pitch]
     size_t pitch = 0;
@@ -124,6 +129,10 @@ struct KernelTimer {
 
 // ---- kernel launchers (launch counting happens in KernelTimer) ------------------------------------------
 void launch_remap(mvsv_ctx* c, int cam, int B);
+void launch_resize(mvsv_ctx* c, int cam, int B);
+// inverse of P[:, :3]*R, camera matrix and distortion of one camera (cv::initUndistortRectifyMap's inputs)
+struct RectifyCoef { double iR[9]; double k1, k2, p1, p2, k3; double fx, fy, cx, cy; };
+void launch_rectify_maps(mvsv_ctx* c, int cam, const RectifyCoef& q);
 void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t stride_elems);
 void launch_sgbm(mvsv_ctx* c, int B);
 void launch_bm(mvsv_ctx* c, int B);

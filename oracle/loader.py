@@ -162,3 +162,32 @@ def dmap_values(c, Q):
     out = np.empty(3, np.float32)
     lib().orc_dmap_values(_p(c, C.c_float), _p(Q, C.c_float), _p(out, C.c_float))
     return out
+
+
+def rectify_maps(K, dist5, R, P, size):
+    """reference src/Stereosystem.cpp:214-217 (cv::initUndistortRectifyMap, CV_32FC1); size = (W, H)."""
+    K = np.ascontiguousarray(K, np.float64).reshape(9)
+    d = np.zeros(5, np.float64)
+    dd = np.asarray(dist5, np.float64).ravel()
+    d[:min(5, dd.size)] = dd[:5]
+    R = np.ascontiguousarray(R, np.float64).reshape(9)
+    P = np.ascontiguousarray(P, np.float64).reshape(12)
+    W, H = size
+    mx = np.empty((H, W), np.float32)
+    my = np.empty((H, W), np.float32)
+    lib().orc_rectify_maps(_p(K, C.c_double), _p(d, C.c_double), _p(R, C.c_double), _p(P, C.c_double), W, H,
+                           _p(mx, C.c_float), _p(my, C.c_float))
+    return mx, my
+
+
+def resize(img, factor):
+    """reference src/Stereosystem.cpp:294-295: cv::resize(img, dst, Size(0,0), factor, factor) for CV_8UC1."""
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    L = lib()
+    L.orc_resize_dim.argtypes = [C.c_int, C.c_double]
+    L.orc_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    dw, dh = L.orc_resize_dim(W, float(factor)), L.orc_resize_dim(H, float(factor))
+    out = np.empty((dh, dw), np.uint8)
+    L.orc_resize(img.ctypes.data, W, H, float(factor), out.ctypes.data)
+    return out

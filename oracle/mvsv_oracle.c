@@ -28,6 +28,8 @@
  *   orc_mean         src/utility.cpp:265-285       Utility::calcMeanDisparity
  *   orc_reproject    src/utility.cpp:176-200,242-262  calcCoordinate / dmap2pcl
  *   orc_dmap_values  src/utility.cpp:224-240       calcDMapValues
+ *   orc_resize       src/Stereosystem.cpp:294-295  cv::resize(roi, dst, Size(0,0), factor, factor), CV_8UC1
+ *   orc_rectify_maps src/Stereosystem.cpp:214-217  cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1)
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -527,4 +529,102 @@ void orc_dmap_values(const float c[3], const float* Q, float out[3])
     out[1] = c[0] * (dv * Q[3 * 4 + 2] * Q[3 * 4 + 3]) + Q[0 * 4 + 3];
     out[2] = c[1] * (dv * Q[3 * 4 + 2] * Q[3 * 4 + 3]) + Q[1 * 4 + 3];
     out[0] = dv * 16;
+}
+
+/* ------------------------------------------------------------------------- */
+/* initUndistortRectifyMap: src/Stereosystem.cpp:214-217 (K, 5 distortion      */
+/* coefficients k1 k2 p1 p2 k3, rectifying rotation R, projection P; CV_32FC1 */
+/* maps).  Double arithmetic, no fused multiply-add (build with               */
+/* -ffp-contract=off), results rounded to float like the reference's maps.    */
+/* ------------------------------------------------------------------------- */
+static void inv3(const double* m, double* o)
+{
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[3] * m[8] - m[5] * m[6], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 - m[1] * c01 + m[2] * c02;
+    const double d = 1.0 / det;
+    o[0] = c00 * d;                          o[1] = (m[2] * m[7] - m[1] * m[8]) * d;  o[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    o[3] = (m[5] * m[6] - m[3] * m[8]) * d;  o[4] = (m[0] * m[8] - m[2] * m[6]) * d;  o[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    o[6] = c02 * d;                          o[7] = (m[1] * m[6] - m[0] * m[7]) * d;  o[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+}
+
+void orc_rectify_maps(const double* K, const double* dist5, const double* R, const double* P /* 3x4 */, int W, int H,
+                      float* mapx, float* mapy)
+{
+    double A[9], iR[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += P[r * 4 + k] * R[k * 3 + c];
+            A[r * 3 + c] = acc;
+        }
+    inv3(A, iR);
+    const double k1 = dist5[0], k2 = dist5[1], p1 = dist5[2], p2 = dist5[3], k3 = dist5[4];
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const double _x = j * iR[0] + i * iR[1] + iR[2], _y = j * iR[3] + i * iR[4] + iR[5], _w = j * iR[6] + i * iR[7] + iR[8];
+            const double x = _x / _w, y = _y / _w;
+            const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            const double kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2;
+            const double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2);
+            const double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy;
+            mapx[(size_t)i * W + j] = (float)(fx * xd + cx);
+            mapy[(size_t)i * W + j] = (float)(fy * yd + cy);
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* cv::resize(src, dst, Size(0,0), f, f), CV_8UC1, INTER_LINEAR (the default): */
+/* src/Stereosystem.cpp:294-295.  dst must hold orc_resize_dim(w, f) x       */
+/* orc_resize_dim(h, f) bytes.  Scale exactly 1/2 takes OpenCV's 2x2 area path. */
+/* ------------------------------------------------------------------------- */
+#include <float.h>
+int orc_resize_dim(int n, double f) { return (int)lrint((double)n * f); }
+
+void orc_resize(const uint8_t* src, int sw, int sh, double f, uint8_t* dst)
+{
+    const int dw = orc_resize_dim(sw, f), dh = orc_resize_dim(sh, f);
+    const double scale = 1.0 / f;
+    const long iscale = lrint(scale);
+    if (fabs(scale - (double)iscale) < DBL_EPSILON && iscale == 2) {
+        for (int dy = 0; dy < dh; ++dy)
+            for (int dx = 0; dx < dw; ++dx) {
+                const int x0 = 2 * dx, y0 = 2 * dy;
+                int sum = 0, cnt = 0;
+                for (int y = y0; y < y0 + 2 && y < sh; ++y)
+                    for (int x = x0; x < x0 + 2 && x < sw; ++x) { sum += src[(size_t)y * sw + x]; ++cnt; }
+                int v;
+                if (cnt == 4) v = (sum + 2) >> 2;
+                else v = cnt ? (int)lrintf((float)sum / (float)cnt) : 0;
+                dst[(size_t)dy * dw + dx] = (uint8_t)v;
+            }
+        return;
+    }
+    int* xofs = (int*)malloc(sizeof(int) * (size_t)dw * 3);
+    int *a0 = xofs + dw, *a1 = xofs + 2 * dw;
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float)((dx + 0.5) * scale - 0.5);
+        int sx = (int)floorf(fx);
+        fx -= (float)sx;
+        if (sx < 0) { sx = 0; fx = 0.f; }
+        if (sx >= sw - 1) { sx = sw - 1; fx = 0.f; }
+        xofs[dx] = sx;
+        a0[dx] = (int)lrintf((1.f - fx) * 2048.f);
+        a1[dx] = (int)lrintf(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale - 0.5);
+        const int sy = (int)floorf(fy);
+        fy -= (float)sy;
+        const int b0 = (int)lrintf((1.f - fy) * 2048.f), b1 = (int)lrintf(fy * 2048.f);
+        const int y0 = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy), y1 = sy + 1 < 0 ? 0 : (sy + 1 > sh - 1 ? sh - 1 : sy + 1);
+        const uint8_t *r0 = src + (size_t)y0 * sw, *r1 = src + (size_t)y1 * sw;
+        for (int dx = 0; dx < dw; ++dx) {
+            const int sx = xofs[dx], x1 = sx + 1 < sw ? sx + 1 : sw - 1;
+            const int s0 = r0[sx] * a0[dx] + r0[x1] * a1[dx], s1 = r1[sx] * a0[dx] + r1[x1] * a1[dx];
+            int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            dst[(size_t)dy * dw + dx] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(xofs);
 }
