@@ -117,6 +117,16 @@ int mvsv_compute(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8
  * that produce frames on the GPU). */
 int mvsv_compute_device(mvsv_ctx* ctx, const uint8_t* dleft, size_t lstride, const uint8_t* dright, size_t rstride,
                         size_t frame_stride, int batch, unsigned stages);
+/* Disparity::tm(Stereopair const&, cv::Mat& output, unsigned kernelSize) (src/disparity.cpp:25-58): for every pixel
+ * (i, j), i < rows-kernelSize, j < cols-kernelSize, the kernelSize x kernelSize block of the left image is matched
+ * by normalised cross-correlation (cv::matchTemplate TM_CCORR_NORMED) against the right image's blocks at
+ * (j + x, i), x in [0, cols-j-kernelSize); out(i, j) = (uint8) x of the first maximum (cv::minMaxLoc), 0 elsewhere.
+ * Synchronous: host images in (rectified size of mvsv_get_info, pair b at base + b*frame_stride), `batch` CV_8U
+ * maps out (map b at out + b*height*ostride).  The ranking is evaluated in exact integer arithmetic; OpenCV's
+ * floating-point scores can order exact ties and last-bit near-ties differently (tests/test_tm.py).
+ * Limits: kernelSize in [1, 31], width <= 4096. */
+int mvsv_tm(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
+            size_t frame_stride, int batch, unsigned kernel_size, uint8_t* out, size_t ostride);
 /* Copy results of the last compute back to host memory and synchronise.  Any pointer may be NULL.
  *   disp  : batch x height x (dstride bytes per row) int16, CV_16S x16 fixed point, INVALID=(minD-1)*16
  *   rectL/R: batch x height x (rstride bytes) uint8

@@ -115,6 +115,26 @@ public:
         return mvsv_download(ctx_, reinterpret_cast<int16_t*>(out.data), out.step, nullptr, nullptr, 0, nullptr, nullptr);
     }
 
+    // Disparity::tm (reference src/disparity.cpp:25-58)
+    int computeTm(const Mat& left, const Mat& right, Mat& out, unsigned kernelSize)
+    {
+        err_.clear();
+        if (left.empty() || right.empty() || left.rows != right.rows || left.cols != right.cols ||
+            left.elemSize() != 1 || right.elemSize() != 1) { err_ = "tm: need two equal-size CV_8UC1 images"; return MVSV_ERR_INVALID; }
+        if (!ctx_ || w_ != left.cols || h_ != left.rows) {
+            mvsv_destroy(ctx_); ctx_ = nullptr;
+            int rc = mvsv_init(device_, left.cols, left.rows, 1, &ctx_);
+            if (rc != MVSV_OK) { err_ = mvsv_last_error(nullptr); return rc; }
+            w_ = left.cols; h_ = left.rows; applied_ = applied_bm_ = false;
+        }
+#ifdef MVSV_WITH_OPENCV
+        out.create(left.rows, left.cols, CV_8UC1);
+#else
+        out.create(left.rows, left.cols, MVSV_8UC1);
+#endif
+        return mvsv_tm(ctx_, left.data, left.step, right.data, right.step, 0, 1, kernelSize, out.data, out.step);
+    }
+
 private:
     int device_;
     mvsv_ctx* ctx_ = nullptr;
@@ -167,6 +187,13 @@ inline void sgbm(Stereopair const& inputImages, mvsv::Mat& output, mvsv::Matcher
 inline void bm(Stereopair const& inputImages, mvsv::Mat& output, mvsv::Matcher& dispCompute)
 {
     dispCompute.compute(inputImages.mLeft, inputImages.mRight, output, MVSV_STAGE_BM);
+}
+
+// reference src/disparity.cpp:25-58 (inc/disparity.h:33): the "self written template matching"; the reference has
+// no matcher object here, the engine handle takes its place as the last argument
+inline void tm(Stereopair const& inputImages, mvsv::Mat& output, unsigned int kernelSize, mvsv::Matcher& engine)
+{
+    engine.computeTm(inputImages.mLeft, inputImages.mRight, output, kernelSize);
 }
 
 // reference src/disparity.cpp:60-108: reads the nine keys, drives the eight setters + mode; never sets P1/P2.

@@ -17,7 +17,7 @@ STAGE_RECTIFY, STAGE_SGBM, STAGE_BM, STAGE_XYZ, STAGE_MEANS = 1, 2, 4, 8, 16
 ABI_SYMBOLS = (
     "mvsv_init", "mvsv_destroy", "mvsv_last_error", "mvsv_set_sgbm_params", "mvsv_set_bm_params",
     "mvsv_upload_rectify_maps", "mvsv_set_rectification", "mvsv_set_resize", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
-    "mvsv_compute_device", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
+    "mvsv_compute_device", "mvsv_tm", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
     "mvsv_host_alloc", "mvsv_host_free", "mvsv_debug_set_flags", "mvsv_debug_read",
     "mvsv_download_minmax", "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
 )
@@ -74,6 +74,7 @@ def load_library():
     lib.mvsv_set_mean_rois.argtypes = [vp, vp, ci]
     lib.mvsv_compute.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint]
     lib.mvsv_compute_device.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint]
+    lib.mvsv_tm.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint, vp, sz]
     lib.mvsv_download.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
     lib.mvsv_sync.argtypes = [vp]
     lib.mvsv_download_minmax.argtypes = [vp, vp]
@@ -247,6 +248,18 @@ class Engine:
     def compute_device(self, dleft_ptr, lstride, dright_ptr, rstride, frame_stride, batch, stages):
         self._ck(self._lib.mvsv_compute_device(self._ctx, dleft_ptr, lstride, dright_ptr, rstride, frame_stride, batch, stages))
 
+    def tm(self, left, right, kernel_size):
+        """Disparity::tm (reference src/disparity.cpp:25-58) on host images [B,]H,W -> uint8 [B,H,W]."""
+        left, right = self._batchify(left), self._batchify(right)
+        if left.shape != right.shape:
+            raise ValueError("left/right shapes differ")
+        if left.strides[0] != right.strides[0] and left.shape[0] > 1:
+            raise ValueError("left/right frame strides differ")
+        out = np.empty(left.shape, np.uint8)
+        self._ck(self._lib.mvsv_tm(self._ctx, left.ctypes.data, left.strides[1], right.ctypes.data, right.strides[1],
+                                   left.strides[0], left.shape[0], int(kernel_size), out.ctypes.data, out.strides[1]))
+        return out
+
     def sync(self):
         self._ck(self._lib.mvsv_sync(self._ctx))
 
@@ -406,6 +419,11 @@ def bm(inputImages, engine):
     """Mirror of Disparity::bm (reference src/disparity.cpp:18-22)."""
     engine.compute(inputImages.mLeft, inputImages.mRight, STAGE_BM)
     return engine.download(1)["disp"][0]
+
+
+def tm(inputImages, engine, kernelSize):
+    """Mirror of Disparity::tm (reference src/disparity.cpp:25-58): CV_8U map, same size as the inputs."""
+    return engine.tm(inputImages.mLeft, inputImages.mRight, kernelSize)[0]
 
 
 def subimage_rois(cols, rows, x_offset=0):

@@ -9,7 +9,7 @@
 
 const char* const kKernelNames[KID_COUNT] = {
     "remap", "sgbm_prefilter", "sgbm_vsum", "sgbm_h1", "sgbm_vdir", "sgbm_td", "sgbm_h2_wta", "median3", "ccl_rows", "ccl_vmerge",
-    "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill", "minmax"};
+    "ccl_flatten", "ccl_apply", "bm_prefilter", "bm_tex", "bm_colsum", "bm_wta", "xyz", "means", "fill", "minmax", "tm"};
 
 namespace {
 
@@ -44,7 +44,7 @@ void free_images(mvsv_ctx* c)
     for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->bm_pre[i]); }
     dfree(c->recL);
     dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
-    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means); dfree(c->minmax);
+    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means); dfree(c->minmax); dfree(c->tm_out);
 }
 void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); dfree(c->plR); c->vol_elems = 0; }
 void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
@@ -488,6 +488,31 @@ int mvsv_set_resize(mvsv_ctx* c, double factor)
     rc = apply_geometry(c);
     if (rc) { c->resize_factor = old; apply_geometry(c); }
     return rc;
+}
+
+int mvsv_tm(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride, size_t frame_stride,
+            int batch, unsigned kernel_size, uint8_t* out, size_t ostride)
+{
+    if (!c || !left || !right || !out) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    const int W = c->W, H = c->H;
+    if (batch < 1 || batch > c->maxB) return fail(c, MVSV_ERR_INVALID, "bad batch size");
+    if (lstride < (size_t)W || rstride < (size_t)W || ostride < (size_t)W) return fail(c, MVSV_ERR_INVALID, "stride smaller than image width");
+    if (kernel_size < 1 || kernel_size > 31) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: kernelSize must be in [1, 31]");
+    if (W > tm_max_width()) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: image wider than 4096");
+    if (tm_smem_bytes(W, (int)kernel_size) > 200 * 1024) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: kernelSize x width exceeds shared memory");
+    rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, W, H, batch, false);
+    if (rc) return rc;
+    rc = upload_images(c, c->rect[1], c->pitch, right, rstride, frame_stride, W, H, batch, false);
+    if (rc) return rc;
+    if (!c->tm_out) MVSV_CK(c, cudaMalloc(&c->tm_out, (size_t)c->maxB * H * c->pitch));
+    MVSV_CK(c, cudaMemsetAsync(c->tm_out, 0, (size_t)batch * H * c->pitch, c->stream));   // cv::Scalar::all(0)
+    // the reference's loops are `i < rows - kernelSize` in unsigned arithmetic: nothing to do unless k < rows, cols
+    if ((int)kernel_size < H && (int)kernel_size < W) MVSV_CK(c, launch_tm(c, batch, (int)kernel_size, c->tm_out, c->pitch));
+    MVSV_CK(c, cudaMemcpy2DAsync(out, ostride, c->tm_out, c->pitch, (size_t)W, (size_t)H * batch, cudaMemcpyDeviceToHost, c->stream));
+    MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    return MVSV_OK;
 }
 
 int mvsv_set_Q(mvsv_ctx* c, const float q[16])

@@ -29,7 +29,7 @@ struct BmNorm {
 enum KernelId {
     KID_REMAP = 0, KID_SGBM_PREFILTER, KID_SGBM_VSUM, KID_SGBM_H1, KID_SGBM_VDIR, KID_SGBM_TD, KID_SGBM_H2_WTA, KID_MEDIAN,
     KID_CCL_ROWS, KID_CCL_VMERGE, KID_CCL_FLATTEN, KID_CCL_APPLY, KID_BM_PREFILTER, KID_BM_TEX, KID_BM_COLSUM,
-    KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_MINMAX, KID_COUNT
+    KID_BM_WTA, KID_XYZ, KID_MEANS, KID_FILL, KID_MINMAX, KID_TM, KID_COUNT
 };
 extern const char* const kKernelNames[KID_COUNT];
 
@@ -60,6 +60,7 @@ struct mvsv_ctx {
     // cv::resize(.., factor, factor) after the crop (Stereosystem::getRectifiedImagepair(sip, factor),
     // reference src/Stereosystem.cpp:279-315); off when resize_factor == 0
     double resize_factor = 0.0;
+    uint8_t* tm_out = nullptr;                // [B][H][pitch], Disparity::tm
     uint8_t* crop[2] = {nullptr, nullptr};    // [B][roi_h][crop_pitch]: remap output when a resize follows
     size_t crop_pitch = 0;
 
@@ -136,6 +137,9 @@ void launch_rectify_maps(mvsv_ctx* c, int cam, const RectifyCoef& q);
 void launch_convert_maps(mvsv_ctx* c, int cam, const float* dmapx, const float* dmapy, size_t stride_elems);
 void launch_sgbm(mvsv_ctx* c, int B);
 void launch_bm(mvsv_ctx* c, int B);
+size_t tm_smem_bytes(int W, int k);
+int tm_max_width();
+cudaError_t launch_tm(mvsv_ctx* c, int B, int k, uint8_t* out, size_t opitch);
 void launch_xyz(mvsv_ctx* c, int B);
 void launch_means(mvsv_ctx* c, int B);
 void launch_minmax(mvsv_ctx* c, int B);

@@ -191,3 +191,15 @@ def resize(img, factor):
     out = np.empty((dh, dw), np.uint8)
     L.orc_resize(img.ctypes.data, W, H, float(factor), out.ctypes.data)
     return out
+
+
+def tm(left, right, kernel_size):
+    """reference src/disparity.cpp:25-58 (Disparity::tm): CV_8U map of the best-correlating offset."""
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    H, W = left.shape
+    out = np.empty((H, W), np.uint8)
+    L = lib()
+    L.orc_tm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_tm(left.ctypes.data, right.ctypes.data, W, H, int(kernel_size), out.ctypes.data)
+    return out

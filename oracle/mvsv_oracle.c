@@ -28,6 +28,7 @@
  *   orc_mean         src/utility.cpp:265-285       Utility::calcMeanDisparity
  *   orc_reproject    src/utility.cpp:176-200,242-262  calcCoordinate / dmap2pcl
  *   orc_dmap_values  src/utility.cpp:224-240       calcDMapValues
+ *   orc_tm           src/disparity.cpp:25-58       Disparity::tm (matchTemplate TM_CCORR_NORMED + minMaxLoc)
  *   orc_resize       src/Stereosystem.cpp:294-295  cv::resize(roi, dst, Size(0,0), factor, factor), CV_8UC1
  *   orc_rectify_maps src/Stereosystem.cpp:214-217  cv::initUndistortRectifyMap(K, D, R, P, size, CV_32FC1)
  */
@@ -627,4 +628,35 @@ void orc_resize(const uint8_t* src, int sw, int sh, double f, uint8_t* dst)
         }
     }
     free(xofs);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Disparity::tm: src/disparity.cpp:25-58.  For every pixel (i, j) with        */
+/* i < rows-k, j < cols-k the k x k block of the left image at (j, i) is       */
+/* matched against the right image's blocks at (j+x, i), x in [0, cols-j-k),   */
+/* by normalised cross-correlation N / sqrt(A * B_x); the output byte is the   */
+/* first x with the largest score.  A is constant per pixel, N >= 0, so the    */
+/* ranking is N^2 / B_x, compared here as exact integers (cv::matchTemplate    */
+/* evaluates it in floating point; see tests/test_tm.py for the tolerance).    */
+/* ------------------------------------------------------------------------- */
+void orc_tm(const uint8_t* left, const uint8_t* right, int W, int H, int k, uint8_t* out)
+{
+    memset(out, 0, (size_t)W * H);
+    if (k < 1 || k >= W || k >= H) return;
+    for (int i = 0; i < H - k; ++i)
+        for (int j = 0; j < W - k; ++j) {
+            uint64_t nb = 0, bb = 1;
+            int bx = 0;
+            for (int x = 0; x < W - j - k; ++x) {
+                uint64_t n = 0, b = 0;
+                for (int v = 0; v < k; ++v)
+                    for (int u = 0; u < k; ++u) {
+                        const uint64_t l = left[(size_t)(i + v) * W + j + u], r = right[(size_t)(i + v) * W + j + x + u];
+                        n += l * r;
+                        b += r * r;
+                    }
+                if ((unsigned __int128)(n * n) * bb > (unsigned __int128)(nb * nb) * b) { nb = n; bb = b; bx = x; }
+            }
+            out[(size_t)i * W + j] = (uint8_t)bx;
+        }
 }
