@@ -139,6 +139,12 @@ int mvsv_download(mvsv_ctx* ctx, int16_t* disp, size_t dstride, uint8_t* rectL, 
  * reference dereferences an end iterator there).  Consumed by the PLY writer's grey ramp (src/ply.cpp:62-95). */
 int mvsv_download_minmax(mvsv_ctx* ctx, int16_t* minmax);
 int mvsv_sync(mvsv_ctx* ctx);
+/* Software pipelining over several engines (one per batch in flight): kernels that later calls submit to `ctx`
+ * start only after everything submitted to `other` so far has finished.  Host->device input copies of `ctx` are not
+ * held back (they run on a separate copy stream), so they -- and `other`'s device->host download -- overlap the
+ * kernels instead of both engines' kernels sharing the GPU and finishing together.  No reference counterpart: the
+ * reference computes one pair per call on the CPU (src/disparity.cpp:6-10). */
+int mvsv_order_after(mvsv_ctx* ctx, mvsv_ctx* other);
 
 int mvsv_get_info(const mvsv_ctx* ctx, mvsv_info* info);
 /* The CUDA stream (cudaStream_t) all work of this ctx is issued on -- for CUDA-event timing by the caller. */

@@ -173,15 +173,24 @@ int upload_images(mvsv_ctx* c, uint8_t* dst, size_t dpitch, const uint8_t* src, 
                   int h, int batch, bool device_src)
 {
     const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaStream_t st = device_src ? c->stream : c->copy_stream;
     if (sstride == (size_t)w && dpitch == (size_t)w && (batch == 1 || frame_stride == (size_t)w * h)) {
-        MVSV_CK(c, cudaMemcpyAsync(dst, src, (size_t)w * h * batch, kind, c->stream));
+        MVSV_CK(c, cudaMemcpyAsync(dst, src, (size_t)w * h * batch, kind, st));
     } else if (frame_stride == sstride * (size_t)h) {
-        MVSV_CK(c, cudaMemcpy2DAsync(dst, dpitch, src, sstride, (size_t)w, (size_t)h * batch, kind, c->stream));
+        MVSV_CK(c, cudaMemcpy2DAsync(dst, dpitch, src, sstride, (size_t)w, (size_t)h * batch, kind, st));
     } else {
         for (int b = 0; b < batch; ++b)
             MVSV_CK(c, cudaMemcpy2DAsync(dst + (size_t)b * h * dpitch, dpitch, src + (size_t)b * frame_stride, sstride, (size_t)w,
-                                         (size_t)h, kind, c->stream));
+                                         (size_t)h, kind, st));
     }
+    return MVSV_OK;
+}
+
+static int inputs_uploaded(mvsv_ctx* c, bool device_src)
+{
+    if (device_src) return MVSV_OK;
+    MVSV_CK(c, cudaEventRecord(c->ev_h2d, c->copy_stream));
+    MVSV_CK(c, cudaStreamWaitEvent(c->stream, c->ev_h2d, 0));
     return MVSV_OK;
 }
 
@@ -196,12 +205,17 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
     if ((stages & MVSV_STAGE_SGBM) && !c->has_sgbm) return fail(c, MVSV_ERR_STATE, "mvsv_set_sgbm_params not called");
     if ((stages & MVSV_STAGE_BM) && !c->has_bm) return fail(c, MVSV_ERR_STATE, "mvsv_set_bm_params not called");
     if ((stages & MVSV_STAGE_XYZ) && !c->has_Q) return fail(c, MVSV_ERR_STATE, "mvsv_set_Q not called");
+    // host inputs: the copies wait for this engine's previous work (which may still read the input buffers), the
+    // kernels wait for the copies
+    if (!device_src) MVSV_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
     if (stages & MVSV_STAGE_RECTIFY) {
         if (!c->has_maps[0] || !c->has_maps[1]) return fail(c, MVSV_ERR_STATE, "rectify maps missing (mvsv_upload_rectify_maps)");
         if (lstride < (size_t)c->fw || rstride < (size_t)c->fw) return fail(c, MVSV_ERR_INVALID, "stride smaller than frame width");
         rc = upload_images(c, c->raw[0], c->raw_pitch, left, lstride, frame_stride, c->fw, c->fh, batch, device_src);
         if (rc) return rc;
         rc = upload_images(c, c->raw[1], c->raw_pitch, right, rstride, frame_stride, c->fw, c->fh, batch, device_src);
+        if (rc) return rc;
+        rc = inputs_uploaded(c, device_src);
         if (rc) return rc;
         for (int cam = 0; cam < 2; ++cam) {
             launch_remap(c, cam, batch);
@@ -212,6 +226,8 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
         rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, c->W, c->H, batch, device_src);
         if (rc) return rc;
         rc = upload_images(c, c->rect[1], c->pitch, right, rstride, frame_stride, c->W, c->H, batch, device_src);
+        if (rc) return rc;
+        rc = inputs_uploaded(c, device_src);
         if (rc) return rc;
     }
     if (stages & MVSV_STAGE_SGBM) {
@@ -229,6 +245,7 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
     }
     if (stages & MVSV_STAGE_MEANS) launch_means(c, batch);
     MVSV_CK(c, cudaGetLastError());
+    MVSV_CK(c, cudaEventRecord(c->ev_done, c->stream));
     c->lastB = batch;
     c->last_stages = stages;
     return MVSV_OK;
@@ -274,6 +291,9 @@ int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv
         return MVSV_ERR_UNSUPPORTED;
     }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (cudaEvent_t* ev : {&c->ev_h2d, &c->ev_done, &c->ev_order})
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = sgbm_configure_kernels()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
     int rc = alloc_images(c);
     if (rc) { g_init_error = c->err; mvsv_destroy(c); return rc; }
@@ -285,6 +305,7 @@ void mvsv_destroy(mvsv_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_images(c);
     free_sgbm_volumes(c);
@@ -296,6 +317,9 @@ void mvsv_destroy(mvsv_ctx* c)
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->stage) cudaFreeHost(c->stage);
+    for (cudaEvent_t ev : {c->ev_h2d, c->ev_done, c->ev_order})
+        if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -502,9 +526,12 @@ int mvsv_tm(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* rig
     if (kernel_size < 1 || kernel_size > 31) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: kernelSize must be in [1, 31]");
     if (W > tm_max_width()) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: image wider than 4096");
     if (tm_smem_bytes(W, (int)kernel_size) > 200 * 1024) return fail(c, MVSV_ERR_UNSUPPORTED, "tm: kernelSize x width exceeds shared memory");
+    MVSV_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
     rc = upload_images(c, c->rect[0], c->pitch, left, lstride, frame_stride, W, H, batch, false);
     if (rc) return rc;
     rc = upload_images(c, c->rect[1], c->pitch, right, rstride, frame_stride, W, H, batch, false);
+    if (rc) return rc;
+    rc = inputs_uploaded(c, false);
     if (rc) return rc;
     if (!c->tm_out) MVSV_CK(c, cudaMalloc(&c->tm_out, (size_t)c->maxB * H * c->pitch));
     MVSV_CK(c, cudaMemsetAsync(c->tm_out, 0, (size_t)batch * H * c->pitch, c->stream));   // cv::Scalar::all(0)
@@ -607,6 +634,19 @@ int mvsv_download_minmax(mvsv_ctx* c, int16_t* minmax)
         minmax[2 * i] = none ? 0 : (int16_t)h[2 * i];
         minmax[2 * i + 1] = none ? 0 : (int16_t)h[2 * i + 1];
     }
+    return MVSV_OK;
+}
+
+int mvsv_order_after(mvsv_ctx* c, mvsv_ctx* other)
+{
+    if (!c || !other) return MVSV_ERR_INVALID;
+    if (c == other) return MVSV_OK;
+    int rc = bind(other);
+    if (rc) return rc;
+    MVSV_CK(other, cudaEventRecord(other->ev_order, other->stream));
+    rc = bind(c);
+    if (rc) return rc;
+    MVSV_CK(c, cudaStreamWaitEvent(c->stream, other->ev_order, 0));
     return MVSV_OK;
 }
 

@@ -38,6 +38,10 @@ struct ProfBracket { int kid; cudaEvent_t a, b; };
 struct mvsv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // host->device input copies run on their own stream so that they overlap kernels of another engine that
+    // mvsv_order_after() has placed in front of this engine's kernels
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_order = nullptr;
     int fw = 0, fh = 0;          // raw frame
     int W = 0, H = 0;            // rectified/cropped pair
     int maxB = 0;
