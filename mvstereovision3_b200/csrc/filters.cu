@@ -118,25 +118,34 @@ __global__ void k_resize_half(const uint8_t* __restrict__ src, size_t spitch, in
 // ------------------------------------------------------------------------------------------------
 // K5: medianBlur(CV_16S, 3), replicate border (inside StereoSGBM::compute)
 // ------------------------------------------------------------------------------------------------
-#define MVSV_CSWAP(a, b) { const int t_ = min(a, b); b = max(a, b); a = t_; }
-__global__ void k_median3(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int H)
+// Row-marching: a lane keeps its column's three rows in registers (one 2-byte load per pixel), sorts them, and takes
+// the neighbouring columns' sorted triples by shuffle; median9 = med3(max of the minima, med of the medians, min of
+// the maxima).  Lanes 0 and 31 only feed neighbours (30 outputs per warp); clamped coordinates give the replicate
+// border.
+constexpr int MED_ROWS = 16, MED_COLS = 30, MED_WARPS = 4;
+__device__ __forceinline__ int med3i(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+__global__ void __launch_bounds__(MED_WARPS * 32)
+k_median3(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int H)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = (blockIdx.x * MED_WARPS + warp) * MED_COLS + lane - 1;
+    const int y0 = blockIdx.y * MED_ROWS, y1 = min(y0 + MED_ROWS, H);
     const int16_t* img = in + (size_t)blockIdx.z * W * H;
-    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
-    const int16_t* r0 = img + (size_t)max(y - 1, 0) * W;
-    const int16_t* r1 = img + (size_t)y * W;
-    const int16_t* r2 = img + (size_t)min(y + 1, H - 1) * W;
-    int p0 = r0[xm], p1 = r0[x], p2 = r0[xp], p3 = r1[xm], p4 = r1[x], p5 = r1[xp], p6 = r2[xm], p7 = r2[x], p8 = r2[xp];
-    MVSV_CSWAP(p1, p2) MVSV_CSWAP(p4, p5) MVSV_CSWAP(p7, p8)
-    MVSV_CSWAP(p0, p1) MVSV_CSWAP(p3, p4) MVSV_CSWAP(p6, p7)
-    MVSV_CSWAP(p1, p2) MVSV_CSWAP(p4, p5) MVSV_CSWAP(p7, p8)
-    MVSV_CSWAP(p0, p3) MVSV_CSWAP(p5, p8) MVSV_CSWAP(p4, p7)
-    MVSV_CSWAP(p3, p6) MVSV_CSWAP(p1, p4) MVSV_CSWAP(p2, p5)
-    MVSV_CSWAP(p4, p7) MVSV_CSWAP(p4, p2) MVSV_CSWAP(p6, p4)
-    MVSV_CSWAP(p4, p2)
-    out[(size_t)blockIdx.z * W * H + (size_t)y * W + x] = (int16_t)p4;
+    int16_t* dst = out + (size_t)blockIdx.z * W * H;
+    const int xc = min(max(x, 0), W - 1);
+    const bool writer = x >= 0 && x < W && lane >= 1 && lane <= MED_COLS;
+    int p0 = img[(size_t)max(y0 - 1, 0) * W + xc], p1 = img[(size_t)y0 * W + xc];
+    for (int y = y0; y < y1; ++y) {
+        const int p2 = img[(size_t)min(y + 1, H - 1) * W + xc];
+        const int lo = min(p0, min(p1, p2)), hi = max(p0, max(p1, p2)), mid = med3i(p0, p1, p2);
+        const int loL = __shfl_up_sync(0xffffffffu, lo, 1), loR = __shfl_down_sync(0xffffffffu, lo, 1);
+        const int miL = __shfl_up_sync(0xffffffffu, mid, 1), miR = __shfl_down_sync(0xffffffffu, mid, 1);
+        const int hiL = __shfl_up_sync(0xffffffffu, hi, 1), hiR = __shfl_down_sync(0xffffffffu, hi, 1);
+        const int m = med3i(max(lo, max(loL, loR)), med3i(mid, miL, miR), min(hi, min(hiL, hiR)));
+        if (writer) dst[(size_t)y * W + x] = (int16_t)m;
+        p0 = p1; p1 = p2;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -196,54 +205,90 @@ __device__ __forceinline__ void ccl_unite(int* L, int a, int b)
     }
 }
 
-__global__ void k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int newVal,
-                             int maxDiff)
+// vmerge / flatten: a thread owns one column of a CCL_ROWS-row strip (a CTA per pixel row would be bound by the CTA
+// launch rate: the per-pixel work is a handful of loads)
+constexpr int CCL_ROWS = 16;
+
+__global__ void __launch_bounds__(128)
+k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ label, int W, int H, int newVal, int maxDiff)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
-    if (x >= W || y >= H) return;
-    const size_t i = ((size_t)blockIdx.z * H + y) * W + x, u = i - W;
-    const int v = img[i], vu = img[u];
-    if (!conn(v, vu, newVal, maxDiff)) return;
-    if (x > 0) {
-        const int vl = img[i - 1], vul = img[u - 1];
-        if (conn(v, vl, newVal, maxDiff) && conn(vu, vul, newVal, maxDiff) && conn(vl, vul, newVal, maxDiff)) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int ya = max((int)blockIdx.y * CCL_ROWS, 1), yb = min(((int)blockIdx.y + 1) * CCL_ROWS, H);
+    if (ya >= yb) return;
+    size_t i = ((size_t)blockIdx.z * H + ya) * W + x;
+    int vu = img[i - W], vul = x > 0 ? img[i - W - 1] : newVal;
+    for (int y = ya; y < yb; ++y, i += W) {
+        const int v = img[i], vl = x > 0 ? img[i - 1] : newVal;
+        if (conn(v, vu, newVal, maxDiff)) {
+            // the left neighbours already link the two rows: skip the redundant union
+            const bool linked = conn(v, vl, newVal, maxDiff) && conn(vu, vul, newVal, maxDiff) && conn(vl, vul, newVal, maxDiff);
+            if (!linked) ccl_unite(label, label[i], label[i - W]);
+        }
+        vu = v; vul = vl;
     }
-    ccl_unite(label, label[i], label[u]);
 }
 
 // One pass after all unions: run starts (the union-find tree nodes) are pointed straight at their root, so that the
 // apply pass finds any pixel's root in at most two hops, and the last pixel of each run adds the run length to the
 // root's size.  Compressing links while other threads still walk them is benign: a link only ever moves to an
 // ancestor (monotone decreasing indices).
-__global__ void k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ sizes, int W,
-                              int H, int newVal, int maxDiff)
+__global__ void __launch_bounds__(128)
+k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __restrict__ sizes, int W, int H, int newVal,
+              int maxDiff)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
-    const size_t rowBase = ((size_t)blockIdx.z * H + y) * W;
-    const size_t i = rowBase + x;
-    const int l = label[i];
-    if (l < 0) return;
-    const int v = img[i];
-    const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
-    const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
-    if (!runStart && !runEnd) return;
-    // label of a run start = tree link; label of the other pixels = their run start
-    const int start = runStart ? (int)i : l;
-    const int root = ccl_find(label, start);
-    if (runStart && l != root) label[i] = root;
-    if (runEnd) atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
+    const int ya = (int)blockIdx.y * CCL_ROWS, yb = min(ya + CCL_ROWS, H);
+    for (int y = ya; y < yb; ++y) {
+        const size_t rowBase = ((size_t)blockIdx.z * H + y) * W;
+        const size_t i = rowBase + x;
+        const int l = label[i];
+        if (l < 0) continue;
+        const int v = img[i];
+        const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
+        const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
+        if (!runStart && !runEnd) continue;
+        // label of a run start = tree link; label of the other pixels = their run start
+        const int start = runStart ? (int)i : l;
+        const int root = ccl_find(label, start);
+        if (runStart && l != root) label[i] = root;
+        if (runEnd) atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
+    }
 }
 
-__global__ void k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const int* __restrict__ label,
-                            const int* __restrict__ sizes, size_t n, int newVal, int maxSize)
+// Eight consecutive pixels per thread (128-bit accesses); pixels of one run share their label, so the root / size
+// lookup is done once per run segment.
+__global__ void __launch_bounds__(256)
+k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const int* __restrict__ label,
+            const int* __restrict__ sizes, size_t n, int newVal, int maxSize)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int l = label[i];
-    if (l < 0) { out[i] = (int16_t)newVal; return; }
-    const int root = ccl_find(label, l);          // <= 2 hops after k_ccl_flatten
-    out[i] = (sizes[root] <= maxSize) ? (int16_t)newVal : img[i];
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= n) return;
+    int l[8];
+    __align__(16) int16_t v[8];
+    const int cnt = (int)min((size_t)8, n - i0);
+    if (cnt == 8) {
+        const int4 la = *reinterpret_cast<const int4*>(label + i0), lb = *reinterpret_cast<const int4*>(label + i0 + 4);
+        l[0] = la.x; l[1] = la.y; l[2] = la.z; l[3] = la.w; l[4] = lb.x; l[5] = lb.y; l[6] = lb.z; l[7] = lb.w;
+        *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(img + i0);
+    } else {
+        for (int k = 0; k < cnt; ++k) { l[k] = label[i0 + k]; v[k] = img[i0 + k]; }
+    }
+    int prev = -2;
+    bool kill = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k >= cnt) break;
+        if (l[k] < 0) { v[k] = (int16_t)newVal; continue; }
+        if (l[k] != prev) {
+            prev = l[k];
+            kill = sizes[ccl_find(label, prev)] <= maxSize;          // <= 2 hops after k_ccl_flatten
+        }
+        if (kill) v[k] = (int16_t)newVal;
+    }
+    if (cnt == 8) *reinterpret_cast<uint4*>(out + i0) = *reinterpret_cast<const uint4*>(v);
+    else for (int k = 0; k < cnt; ++k) out[i0 + k] = v[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -375,7 +420,7 @@ void launch_resize(mvsv_ctx* c, int cam, int B)
 
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
 {
-    dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    dim3 blk(MED_WARPS * 32), grd((c->W + MED_WARPS * MED_COLS - 1) / (MED_WARPS * MED_COLS), (c->H + MED_ROWS - 1) / MED_ROWS, B);
     KernelTimer kt(c, KID_MEDIAN);
     k_median3<<<grd, blk, 0, c->stream>>>(in, out, c->W, c->H);
 }
@@ -387,14 +432,13 @@ void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int ne
     cudaMemsetAsync(c->sizes, 0, n * sizeof(int), c->stream);
     const int nrows = B * H;
     { KernelTimer kt(c, KID_CCL_ROWS); k_ccl_rows<<<(nrows * 32 + 127) / 128, 128, 0, c->stream>>>(img, c->labels, W, nrows, newVal, maxDiff); }
-    dim3 blk(128), grd((W + 127) / 128, H, B);
+    dim3 blk(128), grd((W + 127) / 128, (H + CCL_ROWS - 1) / CCL_ROWS, B);
     if (H > 1) {
-        dim3 grdv((W + 127) / 128, H - 1, B);
         KernelTimer kt(c, KID_CCL_VMERGE);
-        k_ccl_vmerge<<<grdv, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
+        k_ccl_vmerge<<<grd, blk, 0, c->stream>>>(img, c->labels, W, H, newVal, maxDiff);
     }
     { KernelTimer kt(c, KID_CCL_FLATTEN); k_ccl_flatten<<<grd, blk, 0, c->stream>>>(img, c->labels, c->sizes, W, H, newVal, maxDiff); }
-    { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(img, out, c->labels, c->sizes, n, newVal, maxSize); }
+    { KernelTimer kt(c, KID_CCL_APPLY); k_ccl_apply<<<(unsigned)((n + 2047) / 2048), 256, 0, c->stream>>>(img, out, c->labels, c->sizes, n, newVal, maxSize); }
 }
 
 void launch_xyz(mvsv_ctx* c, int B)

@@ -29,52 +29,53 @@ constexpr int vs_compute_threads(int G) { return G >= 16 ? 512 : 256; }
 //                  "address ascending" and every CTA's first entry is 16-byte aligned;
 //   left image  -> one 8-byte record per pixel (a_s, lo_s, hi_s, a_r, lo_r, hi_r, 0, 0).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sob_at(const uint8_t* r0, const uint8_t* r1, const uint8_t* r2, int c, int W, int ftzero)
-{
-    if (c <= 0 || c >= W - 1) return ftzero;
-    int v = 2 * ((int)r1[c + 1] - (int)r1[c - 1]) + ((int)r0[c + 1] - (int)r0[c - 1]) + ((int)r2[c + 1] - (int)r2[c - 1]);
-    v = max(-ftzero, min(ftzero, v));
-    return v + ftzero;
-}
-__device__ __forceinline__ int raw_at(const uint8_t* r1, int c, int W, int ftzero)
-{
-    return (c <= 0 || c >= W - 1) ? ftzero : (int)r1[c];
-}
+// Each warp covers 28 output columns (lanes 2..29; the outer two lanes on either side only feed neighbours) and
+// marches down PF_ROWS rows, loading one byte per lane per row: with s(x) = r0[x] + 2 r1[x] + r2[x] the Sobel
+// response is s(x+1) - s(x-1), so the horizontal taps come from shuffles and the vertical ones from registers.
+constexpr int PF_ROWS = 16, PF_COLS = 28, PF_WARPS = 4;
 
-__global__ void k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch,
-                                 int W, int H, int ftzero, uint2* __restrict__ recL, uint16_t* __restrict__ plR,
-                                 size_t planeStrideR, int RP, int JOFF)
+__global__ void __launch_bounds__(PF_WARPS * 32)
+k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch,
+                 int W, int H, int ftzero, uint2* __restrict__ recL, uint16_t* __restrict__ plR,
+                 size_t planeStrideR, int RP, int JOFF)
 {
-    // 30 output columns per warp: lanes 0 and 31 only supply the neighbours of lanes 1 and 30
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = (blockIdx.x * (blockDim.x >> 5) + warp) * 30 + lane - 1;
-    const int y = blockIdx.y;
+    const int x = (blockIdx.x * PF_WARPS + warp) * PF_COLS + lane - 2;
+    const int y0 = blockIdx.y * PF_ROWS, y1 = min(y0 + PF_ROWS, H);
     const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
     const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
-    const uint8_t* r1 = img + (size_t)y * pitch;
-    const uint8_t* r0 = img + (size_t)max(y - 1, 0) * pitch;
-    const uint8_t* r2 = img + (size_t)min(y + 1, H - 1) * pitch;
-    const bool inimg = x >= 0 && x < W;
-    int a[2] = {0, 0};
-    if (inimg) { a[0] = sob_at(r0, r1, r2, x, W, ftzero); a[1] = raw_at(r1, x, W, ftzero); }
-    int v[6];
+    const int xc = min(max(x, 0), W - 1);                       // out-of-image lanes load a valid byte, results unused
+    const bool inimg = x >= 0 && x < W, border = x <= 0 || x >= W - 1;
+    const bool writer = inimg && lane >= 2 && lane < 2 + PF_COLS;
+    int p0 = img[(size_t)max(y0 - 1, 0) * pitch + xc], p1 = img[(size_t)y0 * pitch + xc];
+    for (int y = y0; y < y1; ++y) {
+        const int p2 = img[(size_t)min(y + 1, H - 1) * pitch + xc];
+        const int sv = p0 + 2 * p1 + p2;
+        const int sl = __shfl_up_sync(FULL, sv, 1), sr = __shfl_down_sync(FULL, sv, 1);
+        int a[2];
+        a[0] = border ? ftzero : max(-ftzero, min(ftzero, sr - sl)) + ftzero;
+        a[1] = border ? ftzero : p1;
+        int v[6];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        const int l = __shfl_up_sync(0xffffffffu, a[ch], 1), r = __shfl_down_sync(0xffffffffu, a[ch], 1);
-        int lo = a[ch], hi = a[ch];
-        if (x > 0) { const int m = (a[ch] + l) >> 1; lo = min(lo, m); hi = max(hi, m); }
-        if (x < W - 1) { const int m = (a[ch] + r) >> 1; lo = min(lo, m); hi = max(hi, m); }
-        v[ch * 3 + 0] = a[ch]; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
-    }
-    if (!inimg || lane == 0 || lane == 31) return;
-    if (im == 0) {
-        recL[((size_t)f * H + y) * W + x] =
-            make_uint2((unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24),
-                       (unsigned)v[4] | ((unsigned)v[5] << 8));
-    } else {
-        uint16_t* o = plR + ((size_t)f * H + y) * RP + (JOFF + W - 1 - x);
-        o[0 * planeStrideR] = (uint16_t)v[0]; o[1 * planeStrideR] = (uint16_t)v[1]; o[2 * planeStrideR] = (uint16_t)(-v[2]);
-        o[3 * planeStrideR] = (uint16_t)v[3]; o[4 * planeStrideR] = (uint16_t)v[4]; o[5 * planeStrideR] = (uint16_t)(-v[5]);
+        for (int ch = 0; ch < 2; ++ch) {
+            const int l = __shfl_up_sync(FULL, a[ch], 1), r = __shfl_down_sync(FULL, a[ch], 1);
+            int lo = a[ch], hi = a[ch];
+            if (x > 0) { const int m = (a[ch] + l) >> 1; lo = min(lo, m); hi = max(hi, m); }
+            if (x < W - 1) { const int m = (a[ch] + r) >> 1; lo = min(lo, m); hi = max(hi, m); }
+            v[ch * 3 + 0] = a[ch]; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
+        }
+        if (writer) {
+            if (im == 0) {
+                recL[((size_t)f * H + y) * W + x] =
+                    make_uint2((unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24),
+                               (unsigned)v[4] | ((unsigned)v[5] << 8));
+            } else {
+                uint16_t* o = plR + ((size_t)f * H + y) * RP + (JOFF + W - 1 - x);
+                o[0 * planeStrideR] = (uint16_t)v[0]; o[1 * planeStrideR] = (uint16_t)v[1]; o[2 * planeStrideR] = (uint16_t)(-v[2]);
+                o[3 * planeStrideR] = (uint16_t)v[3]; o[4 * planeStrideR] = (uint16_t)v[4]; o[5 * planeStrideR] = (uint16_t)(-v[5]);
+            }
+        }
+        p0 = p1; p1 = p2;
     }
 }
 
@@ -1061,7 +1062,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     cudaStream_t st = c->stream;
     const size_t planeStrideR = (size_t)c->maxB * c->H * c->vsRP;
     {
-        dim3 blk(128), grd((c->W + 119) / 120, c->H, 2 * B);      // 4 warps x 30 columns
+        dim3 blk(PF_WARPS * 32), grd((c->W + PF_WARPS * PF_COLS - 1) / (PF_WARPS * PF_COLS), (c->H + PF_ROWS - 1) / PF_ROWS, 2 * B);
         KernelTimer kt(c, KID_SGBM_PREFILTER);
         k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->recL, c->plR,
                                               planeStrideR, c->vsRP, c->vsJOFF);
