@@ -366,6 +366,34 @@ def test_fused_sweep_degenerate_strips(oracle, H, nc):
         check("H=%d nc=%d" % (H, nc), e.download(1)["disp"][0], oracle.sgbm(l, r, p))
 
 
+def test_pipelined_engines_order_after(oracle):
+    """two engines submitting alternately with mvsv_order_after (the e2e pipeline of bench.py): same bits as one"""
+    p = cases.sgbm_params(minDisp=1, numDisp=32, blockSize=5, P1=20, P2=90, uniquenessRatio=5, speckleWindowSize=30, speckleRange=2)
+    H, W, B = 60, 200, 6
+    batches = []
+    for k in range(5):
+        ls, rs = zip(*[synth.random_pair(H, W, seed=100 * k + b) for b in range(B)])
+        batches.append((np.stack(ls), np.stack(rs)))
+    want = [np.stack([oracle.sgbm(L[b], R[b], p) for b in range(B)]) for L, R in batches]
+    engines = [api.Engine(W, H, max_batch=B) for _ in range(2)]
+    try:
+        for e in engines:
+            e.set_sgbm_params(**gpu_params(p))
+        got = [None] * len(batches)
+        engines[0].compute(batches[0][0], batches[0][1], api.STAGE_SGBM)
+        for k in range(1, len(batches)):
+            engines[k & 1].order_after(engines[(k - 1) & 1])
+            engines[k & 1].compute(batches[k][0], batches[k][1], api.STAGE_SGBM)
+            got[k - 1] = engines[(k - 1) & 1].download(B)["disp"]
+        got[-1] = engines[(len(batches) - 1) & 1].download(B)["disp"]
+        engines[0].order_after(engines[0])             # self-ordering is a no-op
+    finally:
+        for e in engines:
+            e.close()
+    for k in range(len(batches)):
+        check("batch %d" % k, got[k], want[k])
+
+
 @pytest.mark.parametrize("nc", [1, 2, 4, 8])
 def test_halo_handoff_soak(oracle, nc):
     """Determinism soak of the st.async + mbarrier halo hand-off: 100 x 24 small MODE_HH frames (two sweeps each)
