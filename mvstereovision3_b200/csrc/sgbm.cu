@@ -931,82 +931,101 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     uint16_t* __restrict__ sp = a.S + rowBase;
     int16_t* __restrict__ drow = a.disp + (size_t)row * a.W;
     int* __restrict__ d2row = a.d2 + (size_t)row * a.W;
-    const int d2init = (MVSV_MAX_COST << 16) | (a.INV & 0xffff);
+    // disp2 entry of right-image column j: (minS << 16) | (W1-1-xi) of the best left pixel xi that maps to j.  The
+    // reference scans x downwards and replaces an entry only by a strictly smaller cost, i.e. it keeps the lowest
+    // cost and among equals the largest x: exactly the minimum of this key, so the scatter is an order-free
+    // atomicMin and the matched disparity is recovered as xi + minX1 - j.
+    constexpr unsigned D2_EMPTY = 0xffffffffu;
     if (active)
-        for (int x = q; x < a.W; x += G) { drow[x] = (int16_t)a.INV; d2row[x] = d2init; }
+        for (int x = q; x < a.W; x += G) { drow[x] = (int16_t)a.INV; d2row[x] = (int)D2_EMPTY; }
     __syncwarp();
 
     unsigned L[4], mm;
     reset_state<PAD>(L, mm, padLane);
     const int umul = 100 - a.uniq;
     const unsigned kb = (unsigned)q * 8u;
-    uint4 CQ[HPF], SQ[HPF];
-#pragma unroll
-    for (int k = 0; k < HPF; ++k) {
-        const int xi = max(W1 - 1 - k, 0);
-        CQ[k] = ld128(cp + xi * Dp); SQ[k] = ld128(sp + xi * Dp);
-    }
-    for (int x0 = W1 - 1; x0 >= 0; x0 -= HPF) {
-        uint4 CQ2[HPF], SQ2[HPF];
-#pragma unroll
-        for (int k = 0; k < HPF; ++k) {
-            const int xn = max(x0 - HPF - k, 0);
-            CQ2[k] = ld128(cp + xn * Dp); SQ2[k] = ld128(sp + xn * Dp);
-        }
-#pragma unroll
-        for (int k = 0; k < HPF; ++k) {
-            const int xi = x0 - k;
-            if (xi < 0) continue;
-            sgm_step<G, PAD>(L, mm, CQ[k], a.P1P1, a.P2P2, q, padLane);
-            unsigned Sf[4];
-            Sf[0] = __viaddmin_u16x2(SQ[k].x, L[0], MVSV_PK_MAX);
-            Sf[1] = __viaddmin_u16x2(SQ[k].y, L[1], MVSV_PK_MAX);
-            Sf[2] = __viaddmin_u16x2(SQ[k].z, L[2], MVSV_PK_MAX);
-            Sf[3] = __viaddmin_u16x2(SQ[k].w, L[3], MVSV_PK_MAX);
-            if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
-            if (a.storeS && active) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
-            // ---- first argmin via (S << 16 | k) keys
-            unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
-                               min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
-            key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
-                               min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
-            const int minS = (int)(key >> 16);
-            const int best = (int)(key & 0xffffu);
-            bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
-            if (a.uniq > 0) {
-                bool bad = false;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int kk = (int)kb + j;
-                    const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
-                    bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
-                }
-                reject |= group_any<G>(bad);
-            }
-            // ---- neighbours of the winner for the parabola
-            const int im = max(best - 1, 0), ip = min(best + 1, a.D - 1);
-            unsigned vm = pick16(Sf, im & 7), vp = pick16(Sf, ip & 7);
-            if (G > 1) {
-                vm = __shfl_sync(FULL, vm, im >> 3, G);
-                vp = __shfl_sync(FULL, vp, ip >> 3, G);
-            }
-            const int sm1 = (int)vm, sp1 = (int)vp;
+    // The per-pixel epilogue (parabola, division, scatter, store) is identical on all G lanes of a pixel, so it is
+    // deferred: lane q keeps the winner of every G-th step and the G lanes finish G pixels at once.
+    unsigned svKey = 0, svM = 0, svP = 0;
+    int svX = -1, sc = 0;
+    auto flush = [&]() {
+        if (svX >= 0) {
+            const int minS = (int)(svKey >> 16), best = (int)(svKey & 0xffffu);
+            const int sm1 = (int)svM, sp1 = (int)svP;
             int v = 16 * best;
             if (best > 0 && best < a.D - 1) {
                 const int den = max(sm1 + sp1 - 2 * minS, 1);
                 v += div_trunc_small((sm1 - sp1) * 16 + den, 2 * den);
             }
-            if (active && q == 0 && !reject) {
-                int* dp = d2row + (xi + a.minX1 - best - a.minD);
-                if ((*dp >> 16) > minS) *dp = (minS << 16) | ((best + a.minD) & 0xffff);
-                drow[xi + a.minX1] = (int16_t)(v + 16 * a.minD);
+            if (active) {
+                atomicMin(reinterpret_cast<unsigned*>(d2row) + (svX + a.minX1 - best - a.minD),
+                          ((unsigned)minS << 16) | (unsigned)(W1 - 1 - svX));
+                drow[svX + a.minX1] = (int16_t)(v + 16 * a.minD);
             }
         }
+        svX = -1;
+    };
+    auto step = [&](const uint4& Cq, const uint4& Sq, int xi) {
+        sgm_step<G, PAD>(L, mm, Cq, a.P1P1, a.P2P2, q, padLane);
+        unsigned Sf[4];
+        Sf[0] = __viaddmin_u16x2(Sq.x, L[0], MVSV_PK_MAX);
+        Sf[1] = __viaddmin_u16x2(Sq.y, L[1], MVSV_PK_MAX);
+        Sf[2] = __viaddmin_u16x2(Sq.z, L[2], MVSV_PK_MAX);
+        Sf[3] = __viaddmin_u16x2(Sq.w, L[3], MVSV_PK_MAX);
+        if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
+        if (a.storeS && active) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
+        // ---- first argmin via (S << 16 | k) keys
+        unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
+                           min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
+        key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
+                           min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
 #pragma unroll
-        for (int k = 0; k < HPF; ++k) { CQ[k] = CQ2[k]; SQ[k] = SQ2[k]; }
+        for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
+        const int minS = (int)(key >> 16);
+        const int best = (int)(key & 0xffffu);
+        bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
+        if (a.uniq > 0) {
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kk = (int)kb + j;
+                const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
+                bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
+            }
+            reject |= group_any<G>(bad);
+        }
+        // ---- neighbours of the winner for the parabola
+        const int im = max(best - 1, 0), ip = min(best + 1, a.D - 1);
+        unsigned vm = pick16(Sf, im & 7), vp = pick16(Sf, ip & 7);
+        if (G > 1) {
+            vm = __shfl_sync(FULL, vm, im >> 3, G);
+            vp = __shfl_sync(FULL, vp, ip >> 3, G);
+        }
+        if (sc == q) { svKey = key; svM = vm; svP = vp; svX = reject ? -1 : xi; }
+        if (++sc == G) { flush(); sc = 0; }
+    };
+    // operands of two steps are held one pair of steps ahead, in two register sets used alternately
+    uint4 CA[HPF], SA[HPF], CB[HPF], SB[HPF];
+    auto fetch = [&](uint4 (&Cd)[HPF], uint4 (&Sd)[HPF], int xfirst) {
+#pragma unroll
+        for (int k = 0; k < HPF; ++k) {
+            const int xn = max(xfirst - k, 0);
+            Cd[k] = ld128(cp + xn * Dp); Sd[k] = ld128(sp + xn * Dp);
+        }
+    };
+    auto run = [&](const uint4 (&Cs)[HPF], const uint4 (&Ss)[HPF], int xfirst) {
+#pragma unroll
+        for (int k = 0; k < HPF; ++k)
+            if (xfirst - k >= 0) step(Cs[k], Ss[k], xfirst - k);
+    };
+    fetch(CA, SA, W1 - 1);
+    for (int x0 = W1 - 1; x0 >= 0; x0 -= 2 * HPF) {
+        fetch(CB, SB, x0 - HPF);
+        run(CA, SA, x0);
+        fetch(CA, SA, x0 - 2 * HPF);
+        run(CB, SB, x0 - HPF);
     }
+    flush();
     __syncwarp();
     if (active) {
         for (int x = a.minX1 + q; x < a.maxX1; x += G) {
@@ -1015,7 +1034,12 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
             const int _d = d1 >> 4, d_ = (d1 + 15) >> 4;
             const int _x = x - _d, x_ = x - d_;
             if (_x < 0 || _x >= a.W || x_ < 0 || x_ >= a.W) continue;
-            const int da = (int)(int16_t)(d2row[_x] & 0xffff), db = (int)(int16_t)(d2row[x_] & 0xffff);
+            // the entries were produced by atomics (performed in L2): read them past L1
+            const unsigned ea = (unsigned)__ldcg(d2row + _x), eb = (unsigned)__ldcg(d2row + x_);
+            // an untouched entry reads as the reference's initial value INVALID_DISP_SCALED = (minD-1)*16, which
+            // passes the `>= minD` test below once minD >= 2 (kept: it is what cv::StereoSGBM computes)
+            const int da = ea == D2_EMPTY ? a.INV : (W1 - 1 - (int)(ea & 0xffffu)) + a.minX1 - _x;
+            const int db = eb == D2_EMPTY ? a.INV : (W1 - 1 - (int)(eb & 0xffffu)) + a.minX1 - x_;
             if (da >= a.minD && abs(da - _d) > a.d12 && db >= a.minD && abs(db - d_) > a.d12) drow[x] = (int16_t)a.INV;
         }
     }
