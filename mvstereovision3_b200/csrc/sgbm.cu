@@ -48,33 +48,42 @@ k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ i
     const bool inimg = x >= 0 && x < W, border = x <= 0 || x >= W - 1;
     const bool writer = inimg && lane >= 2 && lane < 2 + PF_COLS;
     int p0 = img[(size_t)max(y0 - 1, 0) * pitch + xc], p1 = img[(size_t)y0 * pitch + xc];
+    // both channels ride in one register (low half: clipped Sobel, high half: raw), so the half-sample bounds of the
+    // two channels cost one set of packed operations; per-row addresses advance by constants
+    const bool hasL = x > 0, hasR = x < W - 1;
+    const unsigned ftz2 = (unsigned)ftzero * 0x10001u;
+    uint2* rec = recL + ((size_t)f * H + y0) * W + xc;
+    uint16_t* o = plR + ((size_t)f * H + y0) * RP + (JOFF + W - 1 - xc);
+    // the row below is loaded one iteration ahead, so no iteration waits for its own load
+    const uint8_t* nxt = img + (size_t)min(y0 + 1, H - 1) * pitch + xc;
+    int pn = *nxt;
     for (int y = y0; y < y1; ++y) {
-        const int p2 = img[(size_t)min(y + 1, H - 1) * pitch + xc];
+        const int p2 = pn;
+        if (y + 2 < H) nxt += pitch;
+        pn = *nxt;                                              // row min(y + 2, H - 1)
         const int sv = p0 + 2 * p1 + p2;
         const int sl = __shfl_up_sync(FULL, sv, 1), sr = __shfl_down_sync(FULL, sv, 1);
-        int a[2];
-        a[0] = border ? ftzero : max(-ftzero, min(ftzero, sr - sl)) + ftzero;
-        a[1] = border ? ftzero : p1;
-        int v[6];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const int l = __shfl_up_sync(FULL, a[ch], 1), r = __shfl_down_sync(FULL, a[ch], 1);
-            int lo = a[ch], hi = a[ch];
-            if (x > 0) { const int m = (a[ch] + l) >> 1; lo = min(lo, m); hi = max(hi, m); }
-            if (x < W - 1) { const int m = (a[ch] + r) >> 1; lo = min(lo, m); hi = max(hi, m); }
-            v[ch * 3 + 0] = a[ch]; v[ch * 3 + 1] = lo; v[ch * 3 + 2] = hi;
-        }
+        const unsigned sob = (unsigned)(max(-ftzero, min(ftzero, sr - sl)) + ftzero);
+        const unsigned A = border ? ftz2 : (sob | ((unsigned)p1 << 16));
+        const unsigned l = __shfl_up_sync(FULL, A, 1), r = __shfl_down_sync(FULL, A, 1);
+        // (a + neighbour) >> 1 per half: the sums stay below 2^9, so a plain add and a masked shift are exact
+        const unsigned ml = hasL ? (((A + l) >> 1) & 0x7fff7fffu) : A;
+        const unsigned mr = hasR ? (((A + r) >> 1) & 0x7fff7fffu) : A;
+        const unsigned LO = __vminu2(A, __vminu2(ml, mr)), HI = __vmaxu2(A, __vmaxu2(ml, mr));
         if (writer) {
             if (im == 0) {
-                recL[((size_t)f * H + y) * W + x] =
-                    make_uint2((unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24),
-                               (unsigned)v[4] | ((unsigned)v[5] << 8));
+                // bytes: a_s lo_s hi_s a_r | lo_r hi_r 0 0
+                const unsigned w0 = __byte_perm(__byte_perm(A, LO, 0x2040), HI, 0x3410);
+                const unsigned w1 = __byte_perm(LO, HI, 0x4462) & 0xffffu;
+                *rec = make_uint2(w0, w1);
             } else {
-                uint16_t* o = plR + ((size_t)f * H + y) * RP + (JOFF + W - 1 - x);
-                o[0 * planeStrideR] = (uint16_t)v[0]; o[1 * planeStrideR] = (uint16_t)v[1]; o[2 * planeStrideR] = (uint16_t)(-v[2]);
-                o[3 * planeStrideR] = (uint16_t)v[3]; o[4 * planeStrideR] = (uint16_t)v[4]; o[5 * planeStrideR] = (uint16_t)(-v[5]);
+                o[0 * planeStrideR] = (uint16_t)(A & 0xffffu); o[1 * planeStrideR] = (uint16_t)(LO & 0xffffu);
+                o[2 * planeStrideR] = (uint16_t)(0u - (HI & 0xffffu));
+                o[3 * planeStrideR] = (uint16_t)(A >> 16); o[4 * planeStrideR] = (uint16_t)(LO >> 16);
+                o[5 * planeStrideR] = (uint16_t)(0u - (HI >> 16));
             }
         }
+        rec += W; o += RP;
         p0 = p1; p1 = p2;
     }
 }
