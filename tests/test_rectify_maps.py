@@ -263,3 +263,32 @@ def test_resize_odd_roi_and_errors(oracle):
             np.testing.assert_array_equal(out["rectR"][0], oracle.resize(oracle.remap(r, mx, my, roi), f))
         e.reset_rectification()
         assert (e.info.width, e.info.height) == (W, H)
+
+
+@pytest.mark.gpu
+def test_device_maps_4k_frame():
+    """a 3840x2160 frame (BASELINE.json cfg 5 size) with the first rig's calibration scaled up: the device maps still
+    equal cv2's fixed-point maps, and remap + crop through them equals cv2.remap"""
+    cv2 = pytest.importorskip("cv2")
+    from mvstereovision3_b200 import api
+    r = CAL[RIGS[0]]
+    s = 3840 / 752.0
+    size = (3840, 2160)
+    KL, KR = np.array(r["KL"]) * s, np.array(r["KR"]) * s
+    KL[2, 2] = KR[2, 2] = 1.0
+    DL, DR = np.array(r["DL"]), np.array(r["DR"])
+    R0, R1, P0, P1, Q, roi0, roi1 = cv2.stereoRectify(KL, DL, KR, DR, size, np.array(r["R"]), np.array(r["T"]).reshape(3, 1),
+                                                      flags=cv2.CALIB_ZERO_DISPARITY, alpha=0, newImageSize=size)
+    x0, y0 = max(roi0[0], roi1[0]), max(roi0[1], roi1[1])
+    x1, y1 = min(roi0[0] + roi0[2], roi1[0] + roi1[2]), min(roi0[1] + roi0[3], roi1[1] + roi1[3])
+    roi = (x0, y0, x1 - x0, y1 - y0)
+    rng = np.random.default_rng(4)
+    raw = rng.integers(0, 256, (size[1], size[0]), dtype=np.uint8)
+    with api.Engine(size[0], size[1]) as e:
+        for cam, (K, D, R, P) in enumerate(((KL, DL, R0, P0), (KR, DR, R1, P1))):
+            e.set_rectification(cam, K, D, R, P, roi)
+            mx, my = cv2.initUndistortRectifyMap(K, D, R, P, size, cv2.CV_32FC1)
+            np.testing.assert_array_equal(e.read_rectify_map(cam, roi), fixed(mx, my)[y0:y1, x0:x1])
+        e.compute(raw, raw, api.STAGE_RECTIFY)
+        out = e.download(1, disp=False, rect=True)
+        np.testing.assert_array_equal(out["rectR"][0], cv2.remap(raw, mx, my, cv2.INTER_LINEAR)[y0:y1, x0:x1])

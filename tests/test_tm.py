@@ -122,3 +122,17 @@ def test_device_tm_full_frame_properties():
     assert not same.any()
     core = shifted[:475, :752 - 5 - s - 1]
     assert (core == s).mean() > 0.999
+
+
+@pytest.mark.gpu
+def test_device_tm_limits(oracle):
+    """widest supported image (4096 columns) and the largest kernel size against the oracle on a thin strip"""
+    from mvstereovision3_b200 import api
+    H, W = 9, 4096
+    l, r = synth.random_pair(H, W, seed=77)
+    with api.Engine(W, H) as e:
+        np.testing.assert_array_equal(e.tm(l, r, 5)[0], oracle.tm(l, r, 5))
+    with api.Engine(4100, 8) as e:
+        with pytest.raises(api.MvsvError) as ei:
+            e.tm(np.zeros((8, 4100), np.uint8), np.zeros((8, 4100), np.uint8), 5)
+        assert ei.value.code == -5
