@@ -76,6 +76,7 @@ struct mvsv_ctx {
     SgbmNorm sg{};
     int td_nc = 0;               // smallest cluster size of the fused previous-row sweep that fits (0: independent passes)
     unsigned td_nc_mask = 0;     // all cluster sizes that fit (bit = size)
+    int td_nc_cap[5] = {0, 0, 0, 0, 0};   // clusters of size 1, 2, 4, 8, 16 that can be resident at once
     int num_sms = 148;
     mvsv_bm_params bm_raw{};
     BmNorm bm{};

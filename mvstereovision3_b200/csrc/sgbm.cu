@@ -1127,10 +1127,13 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
     { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16, st>>>(a); }
     // throughput: the smallest cluster that fits (clusters of 2 pack the SMs exactly); small batches: more CTAs per
-    // frame as long as the whole grid is still resident at once (single-pair latency 3.3 -> 2.2 ms at cfg 2)
+    // frame as long as all clusters are still resident at once -- up to the non-portable size 16 (single pair: sweep
+    // 1.12 -> 0.62 ms at D = 128, 0.67 -> 0.51 ms at cfg 2)
     int nc = c->td_nc;
-    if (nc > 0 && !((c->debug_flags >> 8) & 0xff))
-        while (((unsigned)(nc << 1) & c->td_nc_mask) && (long long)B * (nc << 1) <= c->num_sms) nc <<= 1;
+    if (nc > 0 && !((c->debug_flags >> 8) & 0xff)) {
+        auto cap = [&](int n) { int i = 0; while ((1 << i) < n) ++i; return c->td_nc_cap[i]; };
+        while (nc < 16 && ((unsigned)(nc << 1) & c->td_nc_mask) && B <= cap(nc << 1)) nc <<= 1;
+    }
     auto vdirs = [&](int bottomUp) {
         if (nc > 0) {
             TdArgs t;
@@ -1231,15 +1234,16 @@ int sgbm_choose_td_cluster(mvsv_ctx* c)
 {
     const SgbmNorm& n = c->sg;
     c->td_nc_mask = 0;
+    for (int& v : c->td_nc_cap) v = 0;
     if (n.W1 <= 0) return 0;
     const int forced = (int)((c->debug_flags >> 8) & 0xff);
     if (forced == 0xff) return 0;
     int smallest = 0;
-    // clusters of 16 (non-portable) fit only a handful at a time: measured slower than the independent passes,
-    // which run at 95 % of HBM peak, so they are used only when forced by the test hook
-    for (int nc = 1; nc <= 16; nc <<= 1) {
+    // clusters of 16 (non-portable) fit only a handful at a time: for throughput they were measured slower than the
+    // independent passes (95 % of HBM peak), so size 16 never becomes the default -- it is only recorded as available
+    // for the small-batch case (or forced by the test hook)
+    for (int nc = 1, idx = 0; nc <= 16; nc <<= 1, ++idx) {
         if (forced && nc != forced) continue;
-        if (!forced && nc > 8) break;
         if (nc > n.W1) break;
         const int Mmax = (n.W1 + nc - 1) / nc;
         const size_t smem = td_smem_bytes(Mmax, n.Dp);
@@ -1255,7 +1259,8 @@ int sgbm_choose_td_cluster(mvsv_ctx* c)
         }
         if (ok > 0) {
             c->td_nc_mask |= (unsigned)nc;
-            if (!smallest) smallest = nc;
+            c->td_nc_cap[idx] = ok;
+            if (!smallest && (forced || nc <= 8)) smallest = nc;
         }
     }
     return smallest;

@@ -1,5 +1,5 @@
 """One warm-up + one timed SGBM step of the bench workload (cfg 2) at a small batch -- the command profiled by ncu.
-usage: python tools/prof_step.py [batch] [cfg]   (cfg: cfg2 | cfg4)"""
+usage: python tools/prof_step.py [batch] [cfg]   (cfg: cfg2 | shipped | cfg4)"""
 import os
 import sys
 
@@ -14,6 +14,10 @@ cfg = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
 if cfg == "cfg2":
     H, W = 480, 752
     p = dict(minDisp=1, numDisp=64, blockSize=13, disp12MaxDiff=0, preFilterCap=0, uniquenessRatio=0,
+             speckleWindowSize=150, speckleRange=2, disparityMode=0, P1=0, P2=0)
+elif cfg == "shipped":
+    H, W = 480, 752
+    p = dict(minDisp=1, numDisp=128, blockSize=13, disp12MaxDiff=0, preFilterCap=0, uniquenessRatio=0,
              speckleWindowSize=150, speckleRange=2, disparityMode=0, P1=0, P2=0)
 else:
     H, W = 1080, 1920
