@@ -101,6 +101,7 @@ struct VsArgs {
     const uint2* recL; const uint16_t* plR; size_t planeStrideR;
     uint16_t* VS;
     int W, H, W1, D, Dp, minD, minX1, SH2, NV, LEN, RP, JOFF;
+    int bandRows;               // output rows per blockIdx.z (== H: one band); a band restarts the vertical sum
 };
 
 __device__ __forceinline__ unsigned bt_pair(unsigned v, unsigned v0, unsigned nv1, unsigned uu, unsigned nuu,
@@ -142,7 +143,7 @@ template <int G> struct VsGeom {
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int G, bool R8>
+template <int G, bool R8, bool BANDS>
 __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
 {
     using GE = VsGeom<G>;
@@ -158,7 +159,10 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
     const int f = blockIdx.y;
     const int xa = blockIdx.x * PX;
     const int bs = 2 * a.SH2 + 1;
-    const int steps = a.H + 2 * a.SH2;
+    // Row band [ya, yb) of this CTA (small batches are split into bands to fill the GPU; a band pays blockSize-1
+    // warm-up rows): step t adds pixel row clamp(t - SH2) and, once bs rows are in, emits output row t - (bs-1)
+    const int ya = BANDS ? blockIdx.z * a.bandRows : 0, yb = BANDS ? min(ya + a.bandRows, a.H) : a.H;
+    const int tb = ya, steps = yb + 2 * a.SH2;
     const size_t rowsR = (size_t)f * a.H;
     // named barriers: 1 + buf = "stage buf is full", 3 + buf = "stage buf is free again"
     constexpr int NTH = GE::THREADS;
@@ -243,12 +247,12 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
             }
         };
 #pragma unroll
-        for (int t0 = 0; t0 < VS_RD - 1; ++t0) issue_loads(t0);
-        for (int t = 0; t < steps; ++t) {
+        for (int t0 = 0; t0 < VS_RD - 1; ++t0) issue_loads(tb + t0);
+        for (int t = tb; t < steps; ++t) {
             const int buf = t & 1;
             issue_loads(t + VS_RD - 1);                        // into the raw slot consumed at step t-1
             cp_async_wait<VS_RD - 1>();                        // row t has landed
-            if (t >= 2) named_bar_sync(3 + buf, NTH);          // compute warps are done with row t-2 (same buffer)
+            if (t - tb >= 2) named_bar_sync(3 + buf, NTH);     // compute warps are done with row t-2 (same buffer)
             store_stage(buf, t);
             named_bar_arrive(1 + buf, NTH);
         }
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
     const int rbase = sh * a.LEN + e0 + sh;                   // + (buf*6 + arr)*8*LEN
     uint4 acc = make_uint4(0, 0, 0, 0);
     int slot = 0;
-    for (int t = 0; t < steps; ++t) {
+    for (int t = tb; t < steps; ++t) {
         const int buf = t & 1;
         named_bar_sync(1 + buf, NTH);
         if (live) {
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
             uint4 old = make_uint4(0, 0, 0, 0);
             if (R8) {
                 uint2* rs = reinterpret_cast<uint2*>(ring) + (size_t)slot * CT + tid;
-                if (t >= bs) {
+                if (t - tb >= bs) {
                     const uint2 o = *rs;
                     old = make_uint4(__byte_perm(o.x, 0, 0x4140), __byte_perm(o.x, 0, 0x4342), __byte_perm(o.y, 0, 0x4140),
                                      __byte_perm(o.y, 0, 0x4342));
@@ -294,11 +298,11 @@ __global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
                 *rs = make_uint2(__byte_perm(pix.x, pix.y, 0x6420), __byte_perm(pix.z, pix.w, 0x6420));
             } else {
                 uint4* rs = reinterpret_cast<uint4*>(ring) + (size_t)slot * CT + tid;
-                if (t >= bs) old = *rs;
+                if (t - tb >= bs) old = *rs;
                 *rs = pix;
             }
             acc.x += pix.x - old.x; acc.y += pix.y - old.y; acc.z += pix.z - old.z; acc.w += pix.w - old.w;
-            if (t >= bs - 1) {
+            if (t - tb >= bs - 1) {
                 const int yo = t - (bs - 1);
                 st128(a.VS + (((size_t)f * a.H + yo) * a.W1 + xi) * a.Dp + q * 8, acc);
             }
@@ -1111,10 +1115,20 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         const size_t smem = (size_t)2 * 6 * 8 * a.LEN * 2 + (size_t)2 * PX * 12 * 4 +
                             (size_t)(2 * n.SH2 + 1) * GE::CT * (r8 ? 8 : 16) +
                             (size_t)VS_RD * GE::IPL * 2 * GE::NPT * 16 + (size_t)VS_RD * GE::RPL * GE::NPT * 8;
-        dim3 grd((n.W1 + PX - 1) / PX, B);
+        // small batches: split the rows into bands until the grid covers the SMs (each band repeats bs-1 rows)
+        const int gx = (n.W1 + PX - 1) / PX, bs = 2 * n.SH2 + 1;
+        int bands = 1;
+        while (bands < 8 && (long long)gx * B * (bands * 2) <= c->num_sms && c->H / (bands * 2) >= 4 * bs) bands *= 2;
+        a.bandRows = (c->H + bands - 1) / bands;
+        dim3 grd(gx, B, (c->H + a.bandRows - 1) / a.bandRows);
         KernelTimer kt(c, KID_SGBM_VSUM);
-        if (r8) k_sgbm_vsum<G, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
-        else k_sgbm_vsum<G, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+        if (bands > 1) {
+            if (r8) k_sgbm_vsum<G, true, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+            else k_sgbm_vsum<G, false, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+        } else {
+            if (r8) k_sgbm_vsum<G, true, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+            else k_sgbm_vsum<G, false, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
+        }
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
@@ -1167,9 +1181,13 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
 template <int G>
 cudaError_t cfg_vsum()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_h1<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
