@@ -216,16 +216,29 @@ k_ccl_vmerge(const int16_t* __restrict__ img, int* __restrict__ label, int W, in
     if (x >= W) return;
     const int ya = max((int)blockIdx.y * CCL_ROWS, 1), yb = min(((int)blockIdx.y + 1) * CCL_ROWS, H);
     if (ya >= yb) return;
-    size_t i = ((size_t)blockIdx.z * H + ya) * W + x;
+    const size_t frameBase = (size_t)blockIdx.z * H * W;
+    size_t i = frameBase + (size_t)ya * W + x;
     int vu = img[i - W], vul = x > 0 ? img[i - W - 1] : newVal;
-    for (int y = ya; y < yb; ++y, i += W) {
-        const int v = img[i], vl = x > 0 ? img[i - 1] : newVal;
-        if (conn(v, vu, newVal, maxDiff)) {
-            // the left neighbours already link the two rows: skip the redundant union
-            const bool linked = conn(v, vl, newVal, maxDiff) && conn(vu, vul, newVal, maxDiff) && conn(vl, vul, newVal, maxDiff);
-            if (!linked) ccl_unite(label, label[i], label[i - W]);
+    constexpr int CH = 4;                                     // rows whose pixel loads are issued together
+    for (int y0 = ya; y0 < yb; y0 += CH) {
+        int v[CH], vl[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const size_t j = frameBase + (size_t)min(y0 + k, yb - 1) * W + x;
+            v[k] = img[j]; vl[k] = x > 0 ? img[j - 1] : newVal;
         }
-        vu = v; vul = vl;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            if (y0 + k >= yb) break;
+            if (conn(v[k], vu, newVal, maxDiff)) {
+                // the left neighbours already link the two rows: skip the redundant union
+                const bool linked = conn(v[k], vl[k], newVal, maxDiff) && conn(vu, vul, newVal, maxDiff) &&
+                                    conn(vl[k], vul, newVal, maxDiff);
+                if (!linked) ccl_unite(label, label[i], label[i - W]);
+            }
+            vu = v[k]; vul = vl[k];
+            i += W;
+        }
     }
 }
 
@@ -240,20 +253,33 @@ k_ccl_flatten(const int16_t* __restrict__ img, int* __restrict__ label, int* __r
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
     const int ya = (int)blockIdx.y * CCL_ROWS, yb = min(ya + CCL_ROWS, H);
-    for (int y = ya; y < yb; ++y) {
-        const size_t rowBase = ((size_t)blockIdx.z * H + y) * W;
-        const size_t i = rowBase + x;
-        const int l = label[i];
-        if (l < 0) continue;
-        const int v = img[i];
-        const bool runStart = (x == 0) || !conn(v, img[i - 1], newVal, maxDiff);
-        const bool runEnd = (x == W - 1) || !conn(v, img[i + 1], newVal, maxDiff);
-        if (!runStart && !runEnd) continue;
-        // label of a run start = tree link; label of the other pixels = their run start
-        const int start = runStart ? (int)i : l;
-        const int root = ccl_find(label, start);
-        if (runStart && l != root) label[i] = root;
-        if (runEnd) atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
+    const size_t frameBase = (size_t)blockIdx.z * H * W;
+    // four rows at a time: all loads of the chunk are issued before any of its (possibly aliasing) label stores, so
+    // they overlap instead of paying one memory latency per row
+    constexpr int CH = 4;
+    for (int y0 = ya; y0 < yb; y0 += CH) {
+        int l[CH], v[CH], vl[CH], vr[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const int y = min(y0 + k, yb - 1);
+            const size_t i = frameBase + (size_t)y * W + x;
+            l[k] = label[i]; v[k] = img[i];
+            vl[k] = x > 0 ? img[i - 1] : newVal; vr[k] = x < W - 1 ? img[i + 1] : newVal;
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            if (y0 + k >= yb || l[k] < 0) continue;
+            const size_t rowBase = frameBase + (size_t)(y0 + k) * W;
+            const size_t i = rowBase + x;
+            const bool runStart = !conn(v[k], vl[k], newVal, maxDiff);
+            const bool runEnd = !conn(v[k], vr[k], newVal, maxDiff);
+            if (!runStart && !runEnd) continue;
+            // label of a run start = tree link; label of the other pixels = their run start
+            const int start = runStart ? (int)i : l[k];
+            const int root = ccl_find(label, start);
+            if (runStart && l[k] != root) label[i] = root;
+            if (runEnd) atomicAdd(&sizes[root], x - (start - (int)rowBase) + 1);
+        }
     }
 }
 
