@@ -61,7 +61,9 @@ typedef struct mvsv_info {
     int sgbm_minX1, sgbm_W1, sgbm_D, sgbm_Dpad, sgbm_npaths;   /* evaluated cost domain          */
     int num_rois;
     int device;
-    int sgbm_td_cluster;             /* CTAs per frame of the fused previous-row sweep (0: independent passes) */
+    int sgbm_td_cluster;             /* column strips (CTAs) per frame of the fused previous-row sweep at max_batch
+                                        (0: independent passes)                                */
+    int last_batch;                  /* stereo pairs of the last compute == frames mvsv_download copies      */
 } mvsv_info;
 
 /* Create an engine on CUDA device `device` for raw frames of frame_width x frame_height, holding up to
@@ -105,11 +107,16 @@ int mvsv_set_Q(mvsv_ctx* ctx, const float q[16]);
 /* ROIs (x, y, w, h quadruples in disparity-map coordinates) whose mean disparity is wanted:
  * the 81 Subimages (src/MeanDisparityDetection.cpp:80-93) and/or the 5x5 Samplepoint windows
  * (src/SamplePointDetection.cpp:38-47), already shifted by the dMapROI offset (trgt/demo.cpp:87-113). */
+/* The ROIs are coordinates of the current disparity-map geometry: a call that changes width/height
+ * (mvsv_upload_rectify_maps, mvsv_set_rectification, mvsv_set_resize, mvsv_reset_rectification) drops them, and
+ * MVSV_STAGE_MEANS then fails with MVSV_ERR_STATE until they are set again. */
 int mvsv_set_mean_rois(mvsv_ctx* ctx, const int* xywh, int n);
 
 /* One pass of the hot path over `batch` stereo pairs held in HOST memory (pair i at base + i*frame_stride).
- * Asynchronous on the ctx stream when the host buffers are pinned (mvsv_host_alloc); pageable buffers are
- * staged through ctx-owned pinned memory.  With MVSV_STAGE_RECTIFY the inputs are raw frames (frame size),
+ * Asynchronous when the host buffers are pinned (mvsv_host_alloc): the copies run on the ctx's copy stream and the
+ * call returns at once.  Pageable buffers are accepted too, but the CUDA driver then stages them itself and the call
+ * returns only when the input copies have been staged (the ctx keeps no staging buffer of its own).  With
+ * MVSV_STAGE_RECTIFY the inputs are raw frames (frame size),
  * otherwise rectified pairs (width x height of mvsv_get_info).  Strides in bytes. */
 int mvsv_compute(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
                  size_t frame_stride, int batch, unsigned stages);
@@ -127,7 +134,8 @@ int mvsv_compute_device(mvsv_ctx* ctx, const uint8_t* dleft, size_t lstride, con
  * Limits: kernelSize in [1, 31], width <= 4096. */
 int mvsv_tm(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8_t* right, size_t rstride,
             size_t frame_stride, int batch, unsigned kernel_size, uint8_t* out, size_t ostride);
-/* Copy results of the last compute back to host memory and synchronise.  Any pointer may be NULL.
+/* Copy results of the last compute back to host memory and synchronise.  Any pointer may be NULL.  The number
+ * of frames copied is that of the last compute (mvsv_info.last_batch): size the buffers for it.
  *   disp  : batch x height x (dstride bytes per row) int16, CV_16S x16 fixed point, INVALID=(minD-1)*16
  *   rectL/R: batch x height x (rstride bytes) uint8
  *   xyz   : batch x height x width x 3 float (0,0,0 where disparity <= 0)
@@ -172,7 +180,7 @@ int mvsv_host_free(void* p);
  * 5 = BM prefiltered left, 6 = BM prefiltered right, 7 / 8 = fixed-point rectification map of camera 0 / 1
  * (roi_h x roi_w int32 pairs: x*32, y*32 rounded).  Returns bytes written or a negative error. */
 /* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
- * bits 8..15: force the cluster size of the fused sweep (1,2,4,8,16; 0xff = force the independent passes). */
+ * bits 8..15: force the number of column strips per frame of the fused sweep (0xff = force the independent passes). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
 long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
 

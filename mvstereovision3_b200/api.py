@@ -43,7 +43,7 @@ class BmParams(C.Structure):
 class Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "frame_width", "frame_height", "width", "height", "max_batch", "sgbm_minX1", "sgbm_W1", "sgbm_D",
-        "sgbm_Dpad", "sgbm_npaths", "num_rois", "device", "sgbm_td_cluster")]
+        "sgbm_Dpad", "sgbm_npaths", "num_rois", "device", "sgbm_td_cluster", "last_batch")]
 
 
 _lib = None
@@ -268,8 +268,14 @@ class Engine:
     def sync(self):
         self._ck(self._lib.mvsv_sync(self._ctx))
 
+    def _check_batch(self, batch, i):
+        # mvsv_download copies the frames of the last compute, whatever the caller's buffers hold
+        if batch != i.last_batch:
+            raise ValueError("download(%d): the last compute held %d stereo pairs" % (batch, i.last_batch))
+
     def download(self, batch, disp=True, rect=False, xyz=False, means=False, out=None):
         i = self.info
+        self._check_batch(batch, i)
         H, W = i.height, i.width
         res = {}
         d = (out["disp"] if out and "disp" in out else np.empty((batch, H, W), np.int16)) if disp else None
@@ -292,6 +298,7 @@ class Engine:
 
     def download_minmax(self, batch):
         """Utility::calcMinMaxDisparity (reference src/utility.cpp:287-304) per frame, reduced on the GPU."""
+        self._check_batch(batch, self.info)
         mm = np.empty((batch, 2), np.int16)
         self._ck(self._lib.mvsv_download_minmax(self._ctx, mm.ctypes.data))
         return mm

@@ -44,9 +44,13 @@ void free_images(mvsv_ctx* c)
     for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->bm_pre[i]); }
     dfree(c->recL);
     dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
-    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->means); dfree(c->minmax); dfree(c->tm_out);
+    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->minmax); dfree(c->tm_out);
 }
-void free_sgbm_volumes(mvsv_ctx* c) { dfree(c->VS); dfree(c->C); dfree(c->S); dfree(c->plR); c->vol_elems = 0; }
+void free_sgbm_volumes(mvsv_ctx* c)
+{
+    dfree(c->VS); dfree(c->C); dfree(c->S); dfree(c->plR); dfree(c->sweep_halo);
+    c->vol_elems = 0;
+}
 void free_bm_volumes(mvsv_ctx* c) { dfree(c->bm_col); c->bm_vol_elems = 0; }
 
 int alloc_images(mvsv_ctx* c)
@@ -56,6 +60,8 @@ int alloc_images(mvsv_ctx* c)
     // host <-> device transfers are single linear copies instead of strided 2-D copies of many short rows
     c->pitch = round_up((size_t)c->W, 16);
     const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
+    // the connected-components labels of the speckle filter are int indices over the whole batch
+    if (nimg >= ((size_t)1 << 31)) return fail(c, MVSV_ERR_UNSUPPORTED, "max_batch * height * width must stay below 2^31 pixels");
     for (int i = 0; i < 2; ++i) {
         MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
         MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg + 64));      // the BM column-sum kernel reads whole aligned words
@@ -79,9 +85,16 @@ int normalise_sgbm(mvsv_ctx* c, const mvsv_sgbm_params* p, SgbmNorm* n)
     n->D = p->numDisp;
     if (n->D <= 0 || n->D % 8 != 0 || n->D > 256)
         return fail(c, MVSV_ERR_INVALID, "numDisp must be a positive multiple of 8 and <= 256");
+    // pixel stride of the volumes = the sweep's lane layout (csrc/sweep.cu): numDisp rounded up to 8, 16 or 32;
+    // the row-scan and cost kernels spread a pixel over the next power of two of lanes (8 disparities each)
+    {
+        int sg, snr;
+        sweep_layout(n->D, &sg, &snr);
+        n->Dp = sg * 2 * snr;
+    }
     int g = 1;
-    while (g * 8 < n->D) g <<= 1;
-    n->G = g; n->Dp = g * 8;
+    while (g * 8 < n->Dp) g <<= 1;
+    n->G = g;
     n->bs = p->blockSize > 0 ? p->blockSize : 5;
     n->SW2 = n->SH2 = n->bs / 2;
     n->ftzero = std::max(p->preFilterCap, 15) | 1;
@@ -125,6 +138,7 @@ int ensure_sgbm_volumes(mvsv_ctx* c)
         MVSV_CK(c, cudaMalloc(&c->S, need * 2));
         c->vol_elems = need;
     }
+    if (!c->sweep_halo) MVSV_CK(c, cudaMalloc(&c->sweep_halo, sweep_scratch_bytes(c)));   // strip-border records of the fused sweep
     if (!c->plR || nv != c->vsNV || rp != c->vsRP || joff != c->vsJOFF) {
         dfree(c->plR);
         const size_t bytes = (size_t)6 * c->maxB * c->H * rp * sizeof(uint16_t);
@@ -205,6 +219,8 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
     if ((stages & MVSV_STAGE_SGBM) && !c->has_sgbm) return fail(c, MVSV_ERR_STATE, "mvsv_set_sgbm_params not called");
     if ((stages & MVSV_STAGE_BM) && !c->has_bm) return fail(c, MVSV_ERR_STATE, "mvsv_set_bm_params not called");
     if ((stages & MVSV_STAGE_XYZ) && !c->has_Q) return fail(c, MVSV_ERR_STATE, "mvsv_set_Q not called");
+    if ((stages & MVSV_STAGE_MEANS) && (c->nrois < 1 || !c->rois || !c->means))
+        return fail(c, MVSV_ERR_STATE, "no mean-disparity ROIs (mvsv_set_mean_rois; a geometry change drops them)");
     // host inputs: the copies wait for this engine's previous work (which may still read the input buffers), the
     // kernels wait for the copies
     if (!device_src) MVSV_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
@@ -285,8 +301,10 @@ int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     c->num_sms = prop.multiProcessorCount;
-    if (prop.major < 10) {
-        g_init_error = "mvsv_init: kernels are built for sm_100a only";
+    if (prop.major != 10 || prop.minor != 0) {
+        // the library holds sm_100a code only (arch-specific, no PTX): other devices have no kernel image
+        g_init_error = "mvsv_init: this library is built for sm_100a (B200, compute capability 10.0) only; device reports " +
+                       std::to_string(prop.major) + "." + std::to_string(prop.minor);
         mvsv_destroy(c);
         return MVSV_ERR_UNSUPPORTED;
     }
@@ -311,12 +329,11 @@ void mvsv_destroy(mvsv_ctx* c)
     free_sgbm_volumes(c);
     free_bm_volumes(c);
     for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); dfree(c->crop[i]); }
-    dfree(c->rois);
+    dfree(c->rois); dfree(c->means);
     for (auto& b : c->brackets) { cudaEventDestroy(b.a); cudaEventDestroy(b.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
-    if (c->stage) cudaFreeHost(c->stage);
     for (cudaEvent_t ev : {c->ev_h2d, c->ev_done, c->ev_order})
         if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -357,23 +374,33 @@ static int resize_rectified(mvsv_ctx* c, int W, int H)
 {
     if (W == c->W && H == c->H) return MVSV_OK;
     MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    // the matcher parameters are re-normalised for the new geometry BEFORE anything is committed: a geometry the
+    // contract rejects (e.g. a frame volume of 2^31 cells) leaves the engine exactly as it was
+    const int oldW = c->W, oldH = c->H;
+    SgbmNorm sg = c->sg;
+    BmNorm bm = c->bm;
     c->W = W; c->H = H;
-    int rc = alloc_images(c);
+    int rc = MVSV_OK;
+    if (c->has_sgbm) rc = normalise_sgbm(c, &c->sgbm_raw, &sg);
+    if (!rc && c->has_bm) rc = normalise_bm(c, &c->bm_raw, &bm);
+    if (rc) { c->W = oldW; c->H = oldH; return rc; }
+    // mean-disparity ROIs are coordinates of the old map: drop them (run() asks for new ones)
+    dfree(c->rois); dfree(c->means);
+    c->nrois = 0;
+    rc = alloc_images(c);
     if (rc) return rc;
     free_sgbm_volumes(c);
     free_bm_volumes(c);
     if (c->has_sgbm) {
-        rc = normalise_sgbm(c, &c->sgbm_raw, &c->sg);
-        if (rc) return rc;
+        c->sg = sg;
         c->td_nc = sgbm_choose_td_cluster(c);
         rc = ensure_sgbm_volumes(c);
-        if (rc) return rc;
+        if (rc) { c->has_sgbm = false; return rc; }
     }
     if (c->has_bm) {
-        rc = normalise_bm(c, &c->bm_raw, &c->bm);
-        if (rc) return rc;
+        c->bm = bm;
         rc = ensure_bm_volumes(c);
-        if (rc) return rc;
+        if (rc) { c->has_bm = false; return rc; }
     }
     return MVSV_OK;
 }
@@ -669,6 +696,7 @@ int mvsv_get_info(const mvsv_ctx* c, mvsv_info* info)
         info->sgbm_npaths = c->sg.npaths;
     }
     info->num_rois = c->nrois; info->device = c->device; info->sgbm_td_cluster = c->has_sgbm ? c->td_nc : 0;
+    info->last_batch = c->lastB;
     return MVSV_OK;
 }
 

@@ -74,9 +74,8 @@ struct mvsv_ctx {
     bool has_sgbm = false, has_bm = false;
     mvsv_sgbm_params sgbm_raw{};
     SgbmNorm sg{};
-    int td_nc = 0;               // smallest cluster size of the fused previous-row sweep that fits (0: independent passes)
-    unsigned td_nc_mask = 0;     // all cluster sizes that fit (bit = size)
-    int td_nc_cap[5] = {0, 0, 0, 0, 0};   // clusters of size 1, 2, 4, 8, 16 that can be resident at once
+    int td_nc = 0;               // strips per frame of the fused previous-row sweep at max_batch (0: independent passes)
+    uint16_t* sweep_halo = nullptr;   // tagged border-pixel records of the strip hand-off (csrc/sweep.cu)
     int num_sms = 148;
     mvsv_bm_params bm_raw{};
     BmNorm bm{};
@@ -108,10 +107,6 @@ struct mvsv_ctx {
     int* rois = nullptr;                      // device [n][4]
     float* means = nullptr;                   // device [B][n]
     int* minmax = nullptr;                    // device [B][2]
-
-    // pinned staging for pageable host buffers
-    uint8_t* stage = nullptr;
-    size_t stage_bytes = 0;
 };
 
 // RAII bracket: records CUDA events on the ctx stream around one kernel launch when profiling is on.
@@ -151,6 +146,12 @@ void launch_minmax(mvsv_ctx* c, int B);
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B);
 void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int newVal, int maxSize, int maxDiff);
 cudaError_t sgbm_configure_kernels();
+// fused previous-row sweep (csrc/sweep.cu): strip decomposition of a batch, scratch sizes, launch
+struct SweepPlan { int NS = 0, NF = 0, Mmax = 0, threads = 0, G = 0, NR = 0; size_t smem = 0; };
+void sweep_layout(int D, int* G, int* NR);
+void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p);
+size_t sweep_scratch_bytes(const mvsv_ctx* c);
+cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp);
 int sgbm_choose_td_cluster(mvsv_ctx* c);
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);
 

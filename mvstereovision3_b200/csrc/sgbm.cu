@@ -12,9 +12,6 @@
 // packed 16x2 (VIADD.16x2 / VIMNMX.U16x2 / VIMNMX3 / VIADDMNMX -- the DPX path on sm_100a).
 #include "mvsv_internal.h"
 
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -362,11 +359,6 @@ __device__ __forceinline__ void reset_state(unsigned (&L)[4], unsigned& mm, bool
     mm = 0u;
 }
 
-__device__ __forceinline__ void ld_state(unsigned (&L)[4], const uint16_t* p)
-{
-    const uint4 v = ld128(p);
-    L[0] = v.x; L[1] = v.y; L[2] = v.z; L[3] = v.w;
-}
 __device__ __forceinline__ void sat_acc(uint4& S, const unsigned (&L)[4])
 {
     S.x = __viaddmin_u16x2(S.x, L[0], MVSV_PK_MAX); S.y = __viaddmin_u16x2(S.y, L[1], MVSV_PK_MAX);
@@ -394,16 +386,18 @@ constexpr int HPF = 2;         // k_sgbm_h2_wta is issue-bound: it keeps a cheap
 template <int G, bool PAD>
 __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
 {
-    constexpr int DP = 8 * G;                       // padded disparity count == a.Dp
+    // a pixel's stride in the volumes is a.Dp <= 8*G: lanes beyond it hold padding only and never touch memory
+    const int DP = a.Dp;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nrows = (long long)a.B * a.H;
     long long row = gtid / G;
     const int q = (int)(gtid % G);
-    const bool active = row < nrows;
-    if (!active) row = nrows - 1;
+    const bool mem = q * 8 < DP;
+    const bool active = row < nrows && mem;
+    if (row >= nrows) row = nrows - 1;
     const bool padLane = q * 8 >= a.D;
     const int W1 = a.W1, SW2 = a.SW2;
-    const size_t rowBase = (size_t)row * W1 * DP + q * 8;
+    const size_t rowBase = (size_t)row * W1 * DP + (mem ? q * 8 : 0);
     const uint16_t* __restrict__ vs = a.VS + rowBase;
     uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
@@ -419,6 +413,7 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
     cp_async_commit();
 #pragma unroll
     for (int k = 0; k < H1_PFD; ++k) { cp_async16(ring + (bs + k) * 128, src(bs + k)); cp_async_commit(); }
+    // (lanes beyond the pixel stride read the first lane's data: valid addresses, values unused)
     cp_async_wait<H1_PFD>();
     uint4 hs = make_uint4(0, 0, 0, 0);
     for (int t = 0; t < bs; ++t) {
@@ -463,8 +458,9 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
     const int f = (int)(col / a.W1);
     int x = (int)(col % a.W1);
     const bool padLane = q * 8 >= a.D;
-    constexpr int DP = 8 * G;
-    const size_t frameBase = (size_t)f * a.H * a.W1 * DP + q * 8;
+    const int DP = a.Dp;
+    const bool mem = q * 8 < DP;
+    const size_t frameBase = (size_t)f * a.H * a.W1 * DP + (mem ? q * 8 : 0);
 
     unsigned L[4], mm;
     reset_state<PAD>(L, mm, padLane);
@@ -476,428 +472,11 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
         if ((dxs < 0 && x == 0) || (dxs > 0 && x == a.W1 - 1)) reset_state<PAD>(L, mm, padLane);
         sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
         sat_acc(Sc, L);
-        if (active) st128(a.S + off, Sc);
+        if (active && mem) st128(a.S + off, Sc);
         x -= dxs;
         if (x >= a.W1) x = 0;
         if (x < 0) x = a.W1 - 1;
     }
-}
-
-// K3b': the three paths that come from the previous row -- r = (-1,dy), (0,dy), (+1,dy) with dy = -1 (top-down)
-// or +1 (bottom-up, MODE_HH) -- fused: C and S are read once and S written once per sweep (6 B/cell instead of 18).
-// One thread-block CLUSTER per frame; CTA r of the cluster owns the column strip [x0, x1).  The path state of the
-// previous row lives in shared memory: the vertical path at slot lx, the diagonals at the skewed slots
-// (lx -/+ y) mod M, so that a pixel's predecessor sits in the very slot the pixel overwrites (in place, no
-// double buffering, no intra-row hazard).  Only the strip's border columns cross CTAs: they are written into the
-// neighbour's halo through distributed shared memory, and one cluster barrier per row orders everything.
-// The C/S vectors of the next work item (also across the row barrier) are prefetched into registers.
-constexpr int TD_THREADS = 512;
-constexpr int TD_SMEM_LIMIT = 200 * 1024;
-// byte offset of the six halo mbarriers behind L | halo[3][2] | m | halom[3][2] (rounded up to 16)
-__host__ __device__ inline size_t td_bar_offset(int Mmax, int Dp)
-{
-    return (((size_t)3 * Mmax * Dp * 2 + (size_t)6 * Dp * 2 + (size_t)3 * Mmax * 4 + 6 * 4) + 15) / 16 * 16;
-}
-
-struct TdArgs {
-    const uint16_t* C; uint16_t* S;
-    int H, W1, D, Dp, NC, Mmax, bottomUp;
-    unsigned P1P1, P2P2;
-};
-
-// Cluster barrier split by memory semantics: only warps that wrote a neighbour's halo (distributed shared memory)
-// arrive with .release (which costs a fence over their outstanding global stores); all other warps arrive
-// .relaxed -- their shared-memory writes are CTA-local and ordered by the preceding __syncthreads().
-__device__ __forceinline__ void cluster_arrive(bool release)
-{
-    if (release) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-template <int G, bool PAD>
-__global__ void __launch_bounds__(TD_THREADS) k_sgbm_td(TdArgs a)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: L[3][Mmax][Dp] u16 | halo[2 parity][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[2][2] u32
-    uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* halo = Lb + (size_t)3 * a.Mmax * a.Dp;
-    unsigned* mb = reinterpret_cast<unsigned*>(halo + 4 * a.Dp);
-    unsigned* halom = mb + 3 * a.Mmax;
-
-    const int r = (int)cluster.block_rank();
-    const int f = blockIdx.y;
-    const int x0 = (int)(((long long)a.W1 * r) / a.NC), x1 = (int)(((long long)a.W1 * (r + 1)) / a.NC);
-    const int M = x1 - x0;
-    constexpr int NG = TD_THREADS / G;
-    const int g = threadIdx.x / G, q = threadIdx.x % G;
-    const bool padLane = q * 8 >= a.D;
-    uint16_t* haloR = (r + 1 < a.NC) ? cluster.map_shared_rank(halo, r + 1) : nullptr;   // CTA owning columns x1..
-    uint16_t* haloL = (r > 0) ? cluster.map_shared_rank(halo, r - 1) : nullptr;
-    unsigned* halomR = (r + 1 < a.NC) ? cluster.map_shared_rank(halom, r + 1) : nullptr;
-    unsigned* halomL = (r > 0) ? cluster.map_shared_rank(halom, r - 1) : nullptr;
-    const int iters = (M + NG - 1) / NG;
-    constexpr int Dp = 8 * G;                       // == a.Dp
-    const int Mmax = a.Mmax, W1 = a.W1;
-    const int rowElems = W1 * Dp;
-    // per-thread base pointers; all further offsets are 32-bit element counts
-    const uint16_t* __restrict__ cbase = a.C + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
-    uint16_t* __restrict__ sbase = a.S + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
-    const int rowStep = a.bottomUp ? -rowElems : rowElems;
-    uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
-    uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
-    uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
-    // warps holding the lane group of the strip's first / last column write the neighbours' halos
-    const bool haloWarp = __any_sync(FULL, (g == 0 && haloL != nullptr) || (g == (M - 1) % NG && haloR != nullptr)) != 0;
-    cluster.sync();     // every CTA of the cluster is resident before any remote shared-memory access
-
-    // work item (yi, it): pixel lx = g + it*NG of row yi; its C/S are loaded one item ahead
-    const int lxFirst = min(g, M - 1);
-    uint4 Cn = ld128(cbase + lxFirst * Dp), Sn = ld128(sbase + lxFirst * Dp);
-    int ymod = 0;       // yi mod M
-    int rowOff = 0;     // yi * rowStep (fits 32 bit: H*W1*Dp < 2^31 is checked on the host)
-    for (int yi = 0; yi < a.H; ++yi) {
-        const int par = yi & 1;
-        const bool firstRow = yi == 0;
-        for (int it = 0; it < iters; ++it) {
-            int lx = g + it * NG;
-            const bool active = lx < M;
-            if (!active) lx = M - 1;
-            const int x = x0 + lx;
-            const int off = rowOff + lx * Dp;
-            const uint4 Cc = Cn;
-            uint4 Sc = Sn;
-            {
-                const bool lastIt = it + 1 == iters;
-                const int nlx = min(lastIt ? g : g + (it + 1) * NG, M - 1);
-                const int noff = (lastIt ? rowOff + rowStep : rowOff) + nlx * Dp;
-                if (!(lastIt && yi + 1 == a.H)) { Cn = ld128(cbase + noff); Sn = ld128(sbase + noff); }
-            }
-            unsigned L[4], mm;
-            // ---- vertical path, slot lx
-            {
-                uint16_t* sl = L1b + lx * Dp;
-                if (firstRow) reset_state<PAD>(L, mm, padLane);
-                else { ld_state(L, sl); mm = mb[Mmax + lx]; }
-                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-                if (active) { st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[Mmax + lx] = mm; }
-                sat_acc(Sc, L);
-            }
-            // ---- diagonal with predecessor (x-1, previous row): slot (lx - yi) mod M, halo from the left CTA
-            {
-                int s1 = lx - ymod; if (s1 < 0) s1 += M;
-                uint16_t* sl = L0b + s1 * Dp;
-                if (firstRow || x == 0) reset_state<PAD>(L, mm, padLane);
-                else if (lx == 0) { ld_state(L, halo + (par * 2 + 0) * Dp + q * 8); mm = halom[par * 2 + 0]; }
-                else { ld_state(L, sl); mm = mb[s1]; }
-                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-                if (active) {
-                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[s1] = mm;
-                    if (lx == M - 1 && haloR) {
-                        st128(haloR + ((par ^ 1) * 2 + 0) * Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
-                        if (q == 0) halomR[(par ^ 1) * 2 + 0] = mm;
-                    }
-                }
-                sat_acc(Sc, L);
-            }
-            // ---- diagonal with predecessor (x+1, previous row): slot (lx + yi) mod M, halo from the right CTA
-            {
-                int s3 = lx + ymod; if (s3 >= M) s3 -= M;
-                uint16_t* sl = L2b + s3 * Dp;
-                if (firstRow || x == W1 - 1) reset_state<PAD>(L, mm, padLane);
-                else if (lx == M - 1) { ld_state(L, halo + (par * 2 + 1) * Dp + q * 8); mm = halom[par * 2 + 1]; }
-                else { ld_state(L, sl); mm = mb[2 * Mmax + s3]; }
-                sgm_step<G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, q, padLane);
-                if (active) {
-                    st128(sl, make_uint4(L[0], L[1], L[2], L[3])); if (q == 0) mb[2 * Mmax + s3] = mm;
-                    if (lx == 0 && haloL) {
-                        st128(haloL + ((par ^ 1) * 2 + 1) * Dp + q * 8, make_uint4(L[0], L[1], L[2], L[3]));
-                        if (q == 0) halomL[(par ^ 1) * 2 + 1] = mm;
-                    }
-                }
-                sat_acc(Sc, L);
-            }
-            if (active) st128(sbase + off, Sc);
-        }
-        if (++ymod == M) ymod = 0;
-        rowOff += rowStep;
-        __syncthreads();
-        cluster_arrive(haloWarp);
-        cluster_wait();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// 16 disparities per lane: lane q of a G2-lane group owns octet q (registers A) and octet q+G2 (registers B) of
-// the pixel (Dp = 16*G2), so that both 128-bit accesses of a warp stay perfectly coalesced.  One recurrence step
-// shares the neighbour shuffles, the min butterfly and all per-pixel bookkeeping between the two octets.
-// ------------------------------------------------------------------------------------------------
-template <int G2, bool PAD>
-__device__ __forceinline__ void sgm_step2(unsigned (&A)[4], unsigned (&B)[4], unsigned& mm, const uint4& Ca, const uint4& Cb,
-                                          unsigned P1P1, unsigned P2P2, int q, bool padA, bool padB)
-{
-    // see sgm_step: neighbours are taken from L + P1 (plain adds), one VIMNMX3 per register
-    const unsigned pa0 = A[0] + P1P1, pa1 = A[1] + P1P1, pa2 = A[2] + P1P1, pa3 = A[3] + P1P1;
-    const unsigned pb0 = B[0] + P1P1, pb1 = B[1] + P1P1, pb2 = B[2] + P1P1, pb3 = B[3] + P1P1;
-    unsigned upA = 0xffffffffu, dnA, upB, dnB = 0xffffffffu;
-    if (G2 > 1) {
-        const int nxt = (q + 1) & (G2 - 1), prv = (q + G2 - 1) & (G2 - 1);
-        const unsigned x = __shfl_sync(FULL, pb0, nxt, G2);     // bottom of octet (q+1)+G2; lane G2-1 gets octet G2
-        const unsigned y = __shfl_sync(FULL, pa0, nxt, G2);     // bottom of octet q+1
-        const unsigned u = __shfl_sync(FULL, pa3, prv, G2);     // top of octet q-1; lane 0 gets octet G2-1
-        const unsigned w = __shfl_sync(FULL, pb3, prv, G2);     // top of octet q-1+G2
-        dnA = (q == G2 - 1) ? x : y;
-        if (q != G2 - 1) dnB = x;
-        if (q != 0) upA = u;
-        upB = (q == 0) ? u : w;
-    } else {
-        dnA = pb0; upB = pa3;
-    }
-    const unsigned mP2 = mm + P2P2;
-    const unsigned XA0 = __byte_perm(upA, pa0, 0x5432), XA1 = __byte_perm(pa0, pa1, 0x5432);
-    const unsigned XA2 = __byte_perm(pa1, pa2, 0x5432), XA3 = __byte_perm(pa2, pa3, 0x5432);
-    const unsigned XA4 = __byte_perm(pa3, dnA, 0x5432);
-    const unsigned XB0 = __byte_perm(upB, pb0, 0x5432), XB1 = __byte_perm(pb0, pb1, 0x5432);
-    const unsigned XB2 = __byte_perm(pb1, pb2, 0x5432), XB3 = __byte_perm(pb2, pb3, 0x5432);
-    const unsigned XB4 = __byte_perm(pb3, dnB, 0x5432);
-    unsigned a0 = __vimin3_u16x2(XA0, XA1, __vminu2(A[0], mP2)) + Ca.x - mm;
-    unsigned a1 = __vimin3_u16x2(XA1, XA2, __vminu2(A[1], mP2)) + Ca.y - mm;
-    unsigned a2 = __vimin3_u16x2(XA2, XA3, __vminu2(A[2], mP2)) + Ca.z - mm;
-    unsigned a3 = __vimin3_u16x2(XA3, XA4, __vminu2(A[3], mP2)) + Ca.w - mm;
-    unsigned b0 = __vimin3_u16x2(XB0, XB1, __vminu2(B[0], mP2)) + Cb.x - mm;
-    unsigned b1 = __vimin3_u16x2(XB1, XB2, __vminu2(B[1], mP2)) + Cb.y - mm;
-    unsigned b2 = __vimin3_u16x2(XB2, XB3, __vminu2(B[2], mP2)) + Cb.z - mm;
-    unsigned b3 = __vimin3_u16x2(XB3, XB4, __vminu2(B[3], mP2)) + Cb.w - mm;
-    if (PAD && padA) { a0 = a1 = a2 = a3 = MVSV_PK_MAX; }
-    if (PAD && padB) { b0 = b1 = b2 = b3 = MVSV_PK_MAX; }
-    unsigned m = __vimin3_u16x2(__vimin3_u16x2(a0, a1, a2), __vimin3_u16x2(a3, b0, b1), __vimin3_u16x2(b2, b3, b3));
-#pragma unroll
-    for (int o = G2 / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G2));
-    mm = __vminu2(m, __byte_perm(m, 0, 0x1032));
-    A[0] = a0; A[1] = a1; A[2] = a2; A[3] = a3;
-    B[0] = b0; B[1] = b1; B[2] = b2; B[3] = b3;
-}
-
-template <bool PAD>
-__device__ __forceinline__ void reset_state2(unsigned (&A)[4], unsigned (&B)[4], unsigned& mm, bool padA, bool padB)
-{
-    const unsigned va = (PAD && padA) ? MVSV_PK_MAX : 0u, vb = (PAD && padB) ? MVSV_PK_MAX : 0u;
-    A[0] = A[1] = A[2] = A[3] = va;
-    B[0] = B[1] = B[2] = B[3] = vb;
-    mm = 0u;
-}
-
-// ---- point-to-point halo hand-off between the CTAs of a cluster: asynchronous remote stores (st.async) that
-// complete a transaction count on an mbarrier in the RECEIVER's shared memory.  Only the lane group that needs a
-// halo ever waits; there is no cluster-wide barrier (and no release fence over outstanding global stores) in the
-// row loop.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned cta)
-{
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(unsigned raddr, const uint4& v, unsigned rbar)
-{
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
-                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ void st_async_b32(unsigned raddr, unsigned v, unsigned rbar)
-{
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
-}
-
-// K3b'' -- the fused previous-row sweep (see k_sgbm_td above for the scheme) with 16 disparities per lane.
-constexpr int TD2_THREADS = 512;      // launch bound; the launcher picks 256 or 512 threads per CTA
-
-template <int G2, bool PAD>
-__global__ void __launch_bounds__(TD2_THREADS) k_sgbm_td2(TdArgs a)
-{
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: L[3][Mmax][Dp] u16 | halo[3 slots][2 dir][Dp] u16 | m[3][Mmax] u32 | halom[3][2] u32 | bars[3][2] u64
-    // Halo slots are triple buffered (row y reads slot y % 3, a sender in row y fills slot (y+1) % 3): a neighbour
-    // can be at most one row ahead, so the slot it fills is never the one still being read.
-    constexpr int Dp = 16 * G2;                     // == a.Dp
-    constexpr int OB = 8 * G2;                      // element offset of the lane's second octet
-    // Bank-conflict swizzle of the state slots: a quarter-warp phase (8 lanes) covers 8/G2 pixels that each touch
-    // one half (16*G2 bytes) of their slot; slots of 32*G2 bytes repeat every 4/G2 pixels in the 128-byte bank
-    // space, so the two halves are exchanged for every other group of 4/G2 slots.  Keyed on the slot index, hence
-    // the same for the writer and the reader of a slot.
-    constexpr int SWS = (G2 == 4) ? 0 : (G2 == 2) ? 1 : (G2 == 1) ? 2 : -1;
-    auto offA = [&](int slot) { return (SWS >= 0 && ((slot >> (SWS < 0 ? 0 : SWS)) & 1)) ? OB : 0; };
-    uint16_t* Lb = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* halo = Lb + (size_t)3 * a.Mmax * Dp;
-    unsigned* mb = reinterpret_cast<unsigned*>(halo + 6 * Dp);
-    unsigned* halom = mb + 3 * a.Mmax;
-    // bars[slot][dir]: completes when the halo of that slot/direction has fully arrived (16-byte aligned region)
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + td_bar_offset(a.Mmax, Dp));
-
-    const int r = (int)cluster.block_rank();
-    const int f = blockIdx.y;
-    const int x0 = (int)(((long long)a.W1 * r) / a.NC), x1 = (int)(((long long)a.W1 * (r + 1)) / a.NC);
-    const int M = x1 - x0;
-    const int NG = blockDim.x / G2;
-    const int g = threadIdx.x / G2, q = threadIdx.x % G2;
-    const bool padA = q * 8 >= a.D, padB = (q + G2) * 8 >= a.D;
-    const bool hasL = r > 0, hasR = r + 1 < a.NC;
-    // shared::cluster addresses of the neighbours' halo / halom / mbarrier arrays (same layout in every CTA)
-    const unsigned rHalo = hasR ? mapa_u32(smem_u32(halo), r + 1) : 0u, lHalo = hasL ? mapa_u32(smem_u32(halo), r - 1) : 0u;
-    const unsigned rHalom = hasR ? mapa_u32(smem_u32(halom), r + 1) : 0u, lHalom = hasL ? mapa_u32(smem_u32(halom), r - 1) : 0u;
-    const unsigned rBars = hasR ? mapa_u32(smem_u32(bars), r + 1) : 0u, lBars = hasL ? mapa_u32(smem_u32(bars), r - 1) : 0u;
-    const unsigned haloBytes = Dp * 2 + 4;          // one pixel's path costs + its packed minimum
-    const int iters = (M + NG - 1) / NG;
-    const int Mmax = a.Mmax, W1 = a.W1;
-    const int rowElems = W1 * Dp;
-    const uint16_t* __restrict__ cbase = a.C + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
-    uint16_t* __restrict__ sbase = a.S + ((size_t)f * a.H + (a.bottomUp ? a.H - 1 : 0)) * rowElems + (size_t)x0 * Dp + q * 8;
-    const int rowStep = a.bottomUp ? -rowElems : rowElems;
-    uint16_t* const L0b = Lb + q * 8;                               // diagonal from x-1
-    uint16_t* const L1b = Lb + Mmax * Dp + q * 8;                   // vertical
-    uint16_t* const L2b = Lb + 2 * Mmax * Dp + q * 8;               // diagonal from x+1
-    if (!PAD) {
-        // "No predecessor" is the state (L = 0, m = 0).  Zero every slot once (first row) and both halos (the
-        // frame's left / right border never receives a neighbour's write), so the row loop needs no reset tests.
-        const int nwords = (3 * Mmax * Dp + 6 * Dp) / 2 + 3 * Mmax + 6;     // L, halo (u16 pairs), m, halom
-        unsigned* wz = reinterpret_cast<unsigned*>(smem_raw);
-        for (int i = threadIdx.x; i < nwords; i += blockDim.x) wz[i] = 0u;
-    }
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 6; ++i) mbar_init(smem_u32(bars + i), 1);
-        // arm the first phase of every halo that will be received: slot p, direction d = bars[p*2 + d]
-        for (int pp = 0; pp < 3; ++pp) {
-            if (hasL) mbar_expect_tx(smem_u32(bars + pp * 2 + 0), haloBytes);
-            if (hasR) mbar_expect_tx(smem_u32(bars + pp * 2 + 1), haloBytes);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    cluster.sync();     // every CTA of the cluster is resident, zeroed and armed before any remote access
-    const int lxFirst = min(g, M - 1);
-    uint4 CnA = ld128(cbase + lxFirst * Dp), CnB = ld128(cbase + lxFirst * Dp + OB);
-    uint4 SnA = ld128(sbase + lxFirst * Dp), SnB = ld128(sbase + lxFirst * Dp + OB);
-    int ymod = 0, rowOff = 0;
-    for (int yi = 0; yi < a.H; ++yi) {
-        const int par = yi % 3, parNext = (yi + 1) % 3;      // halo slot read in this row / filled for the next row
-        const bool firstRow = yi == 0;
-        for (int it = 0; it < iters; ++it) {
-            int lx = g + it * NG;
-            const bool active = lx < M;
-            if (!active) lx = M - 1;
-            const int x = x0 + lx;
-            const int off = rowOff + lx * Dp;
-            const uint4 CcA = CnA, CcB = CnB;
-            uint4 ScA = SnA, ScB = SnB;
-            {
-                const bool lastIt = it + 1 == iters;
-                const int nlx = min(lastIt ? g : g + (it + 1) * NG, M - 1);
-                const int noff = (lastIt ? rowOff + rowStep : rowOff) + nlx * Dp;
-                if (!(lastIt && yi + 1 == a.H)) {
-                    CnA = ld128(cbase + noff); CnB = ld128(cbase + noff + OB);
-                    SnA = ld128(sbase + noff); SnB = ld128(sbase + noff + OB);
-                }
-            }
-            unsigned A[4], B[4], mm;
-            // ---- vertical path, slot lx
-            {
-                uint16_t* sl = L1b + lx * Dp;
-                const int oa = offA(lx), ob = OB - oa;
-                ld_state(A, sl + oa); ld_state(B, sl + ob); mm = mb[Mmax + lx];
-                if (PAD && firstRow) reset_state2<PAD>(A, B, mm, padA, padB);
-                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
-                if (active) {
-                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
-                    if (q == 0) mb[Mmax + lx] = mm;
-                }
-                sat_acc(ScA, A); sat_acc(ScB, B);
-            }
-            // ---- diagonal with predecessor (x-1, previous row): slot (lx - yi) mod M, halo from the left CTA
-            {
-                int s1 = lx - ymod; if (s1 < 0) s1 += M;
-                uint16_t* sl = L0b + s1 * Dp;
-                const bool fromHalo = lx == 0;
-                const int oa = offA(s1), ob = OB - oa;
-                if (active && fromHalo && hasL && yi > 0) {
-                    // halo slot `par` was filled by the left CTA during its row yi-1: use n of this slot
-                    const int n = (yi - 1) / 3;
-                    mbar_wait(smem_u32(bars + par * 2 + 0), n & 1);
-                }
-                const uint16_t* src = fromHalo ? halo + (par * 2 + 0) * Dp + q * 8 : sl;
-                ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 0] : mb[s1];
-                if (active && fromHalo && hasL && yi > 0 && q == 0 && yi + 3 < a.H)
-                    mbar_expect_tx(smem_u32(bars + par * 2 + 0), haloBytes);                                // arm the next use
-                if (PAD && (firstRow || x == 0)) reset_state2<PAD>(A, B, mm, padA, padB);
-                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
-                if (active) {
-                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
-                    if (q == 0) mb[s1] = mm;
-                    if (lx == M - 1 && hasR && yi + 1 < a.H) {
-                        const int hs = parNext * 2 + 0;
-                        const unsigned h = rHalo + (hs * Dp + q * 8) * 2, rb = rBars + hs * 8;
-                        st_async_v4(h, make_uint4(A[0], A[1], A[2], A[3]), rb);
-                        st_async_v4(h + OB * 2, make_uint4(B[0], B[1], B[2], B[3]), rb);
-                        if (q == 0) st_async_b32(rHalom + hs * 4, mm, rb);
-                    }
-                }
-                sat_acc(ScA, A); sat_acc(ScB, B);
-            }
-            // ---- diagonal with predecessor (x+1, previous row): slot (lx + yi) mod M, halo from the right CTA
-            {
-                int s3 = lx + ymod; if (s3 >= M) s3 -= M;
-                uint16_t* sl = L2b + s3 * Dp;
-                const bool fromHalo = lx == M - 1;
-                const int oa = offA(s3), ob = OB - oa;
-                if (active && fromHalo && hasR && yi > 0) {
-                    const int n = (yi - 1) / 3;
-                    mbar_wait(smem_u32(bars + par * 2 + 1), n & 1);
-                }
-                const uint16_t* src = fromHalo ? halo + (par * 2 + 1) * Dp + q * 8 : sl;
-                ld_state(A, src + (fromHalo ? 0 : oa)); ld_state(B, src + (fromHalo ? OB : ob)); mm = fromHalo ? halom[par * 2 + 1] : mb[2 * Mmax + s3];
-                if (active && fromHalo && hasR && yi > 0 && q == 0 && yi + 3 < a.H)
-                    mbar_expect_tx(smem_u32(bars + par * 2 + 1), haloBytes);
-                if (PAD && (firstRow || x == W1 - 1)) reset_state2<PAD>(A, B, mm, padA, padB);
-                sgm_step2<G2, PAD>(A, B, mm, CcA, CcB, a.P1P1, a.P2P2, q, padA, padB);
-                if (active) {
-                    st128(sl + oa, make_uint4(A[0], A[1], A[2], A[3])); st128(sl + ob, make_uint4(B[0], B[1], B[2], B[3]));
-                    if (q == 0) mb[2 * Mmax + s3] = mm;
-                    if (lx == 0 && hasL && yi + 1 < a.H) {
-                        const int hs = parNext * 2 + 1;
-                        const unsigned h = lHalo + (hs * Dp + q * 8) * 2, lb = lBars + hs * 8;
-                        st_async_v4(h, make_uint4(A[0], A[1], A[2], A[3]), lb);
-                        st_async_v4(h + OB * 2, make_uint4(B[0], B[1], B[2], B[3]), lb);
-                        if (q == 0) st_async_b32(lHalom + hs * 4, mm, lb);
-                    }
-                }
-                sat_acc(ScA, A); sat_acc(ScB, B);
-            }
-            if (active) { st128(sbase + off, ScA); st128(sbase + off + OB, ScB); }
-        }
-        if (++ymod == M) ymod = 0;
-        rowOff += rowStep;
-        __syncthreads();        // the row's slot updates are visible CTA-wide; neighbours are paced by the mbarriers
-    }
-    cluster.sync();             // no CTA may exit while a neighbour could still address its shared memory
 }
 
 // K3c + K4: right-to-left path r=(+1,0) fused with winner-take-all, uniqueness, sub-pixel interpolation,
@@ -937,9 +516,10 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     const bool active = row < nrows;
     if (!active) row = nrows - 1;
     const bool padLane = q * 8 >= a.D;
-    constexpr int Dp = 8 * G;                       // == a.Dp
+    const int Dp = a.Dp;                            // pixel stride of the volumes (<= 8*G; lanes beyond it hold padding)
+    const bool mem = q * 8 < Dp;
     const int W1 = a.W1;
-    const size_t rowBase = (size_t)row * W1 * Dp + q * 8;
+    const size_t rowBase = (size_t)row * W1 * Dp + (mem ? q * 8 : 0);
     const uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
     int16_t* __restrict__ drow = a.disp + (size_t)row * a.W;
@@ -986,7 +566,7 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
         Sf[2] = __viaddmin_u16x2(Sq.z, L[2], MVSV_PK_MAX);
         Sf[3] = __viaddmin_u16x2(Sq.w, L[3], MVSV_PK_MAX);
         if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
-        if (a.storeS && active) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
+        if (a.storeS && active && mem) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
         // ---- first argmin via (S << 16 | k) keys
         unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
                            min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
@@ -1064,34 +644,6 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
-// threads per CTA of the 16-disparity sweep: 512 when the strip gives every lane group >= 2 pixels per row
-inline int td2_threads(int Mmax, int G2)
-{
-    // The row barrier waits for the lane groups with the most pixels, so pick the CTA size (<= 512 threads,
-    // whole warps) whose groups all get (almost) the same number k of pixels: largest size with >= 93 % of the
-    // group-iterations doing useful work; e.g. 344 columns x 4 lanes -> 480 threads (120 groups x 3 = 360 slots).
-    int best = (Mmax * G2 >= 1024) ? 512 : 256;
-    double bestEff = 0.0;
-    {
-        const int groups = best / G2, k = (Mmax + groups - 1) / groups;
-        bestEff = (double)Mmax / ((double)groups * k);
-    }
-    if (bestEff >= 0.93) return best;
-    for (int k = 1; k <= 16; ++k) {
-        const int groups = (Mmax + k - 1) / k;
-        int threads = (groups * G2 + 31) / 32 * 32;
-        if (threads > 512 || threads < 128) continue;
-        const double eff = (double)Mmax / ((double)(threads / G2) * k);
-        if (eff >= 0.93) return threads;          // smallest k = most threads first
-    }
-    return best;
-}
-
-inline size_t td_smem_bytes(int Mmax, int Dp)
-{
-    return td_bar_offset(Mmax, Dp) + 6 * 8;
-}
-
 template <int G, bool PAD>
 void launch_sgbm_g(mvsv_ctx* c, int B)
 {
@@ -1140,33 +692,15 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
     { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16, st>>>(a); }
-    // throughput: the smallest cluster that fits (clusters of 2 pack the SMs exactly); small batches: more CTAs per
-    // frame as long as all clusters are still resident at once -- up to the non-portable size 16 (single pair: sweep
-    // 1.12 -> 0.62 ms at D = 128, 0.67 -> 0.51 ms at cfg 2)
-    int nc = c->td_nc;
-    if (nc > 0 && !((c->debug_flags >> 8) & 0xff)) {
-        auto cap = [&](int n) { int i = 0; while ((1 << i) < n) ++i; return c->td_nc_cap[i]; };
-        while (nc < 16 && ((unsigned)(nc << 1) & c->td_nc_mask) && B <= cap(nc << 1)) nc <<= 1;
+    // the three previous-row paths: fused strip sweep (csrc/sweep.cu); independent passes only when it cannot run
+    SweepPlan plan;
+    {
+        const int forced = (int)((c->debug_flags >> 8) & 0xff);
+        if (forced != 0xff) sweep_plan(c, B, forced, &plan);
     }
     auto vdirs = [&](int bottomUp) {
-        if (nc > 0) {
-            TdArgs t;
-            t.C = c->C; t.S = c->S; t.H = c->H; t.W1 = n.W1; t.D = n.D; t.Dp = n.Dp; t.NC = nc; t.Mmax = (n.W1 + nc - 1) / nc;
-            t.bottomUp = bottomUp; t.P1P1 = a.P1P1; t.P2P2 = a.P2P2;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(nc, B, 1); cfg.blockDim = dim3(TD_THREADS, 1, 1);
-            cfg.dynamicSmemBytes = td_smem_bytes(t.Mmax, n.Dp); cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            KernelTimer kt(c, KID_SGBM_TD);
-            if constexpr (G >= 2) {
-                cfg.blockDim = dim3(td2_threads(t.Mmax, G / 2), 1, 1);
-                cudaLaunchKernelEx(&cfg, k_sgbm_td2<G / 2, PAD>, t);
-            } else {
-                cudaLaunchKernelEx(&cfg, k_sgbm_td<G, PAD>, t);
-            }
+        if (plan.NS > 0) {
+            launch_sweep(c, B, plan, bottomUp);
         } else {
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
@@ -1193,42 +727,7 @@ cudaError_t cfg_vsum()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_h1<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_td<G, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_td<G, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-    if constexpr (G >= 2) {
-        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM_LIMIT);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_sgbm_td2<G / 2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
-    }
     return cudaSuccess;
-}
-
-template <int G>
-int td_max_clusters(int nc, size_t smem, int Mmax)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nc, 1, 1); cfg.blockDim = dim3(G >= 2 ? td2_threads(Mmax, G / 2) : TD_THREADS, 1, 1); cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    cudaError_t e;
-    if constexpr (G >= 2) e = cudaOccupancyMaxActiveClusters(&n, k_sgbm_td2<G / 2, false>, &cfg);
-    else e = cudaOccupancyMaxActiveClusters(&n, k_sgbm_td<G, false>, &cfg);
-    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
 }
 
 }  // namespace
@@ -1245,50 +744,22 @@ cudaError_t sgbm_configure_kernels()
     return cudaSuccess;
 }
 
-// Cluster size for the fused previous-row sweep: the smallest power of two whose column strip fits in shared
-// memory (clusters of 2 pack the 148 SMs exactly; clusters of 4 strand 16 of them, measured).
-// 0 = does not fit (or clusters unavailable): fall back to the three independent k_sgbm_vdir passes.
+// Strips per frame the fused previous-row sweep uses for a full batch (reported by mvsv_get_info);
+// 0 = it cannot run (volume stride differs from the sweep's lane layout, or forced off): independent passes.
 int sgbm_choose_td_cluster(mvsv_ctx* c)
 {
-    const SgbmNorm& n = c->sg;
-    c->td_nc_mask = 0;
-    for (int& v : c->td_nc_cap) v = 0;
-    if (n.W1 <= 0) return 0;
     const int forced = (int)((c->debug_flags >> 8) & 0xff);
     if (forced == 0xff) return 0;
-    int smallest = 0;
-    // clusters of 16 (non-portable) fit only a handful at a time: for throughput they were measured slower than the
-    // independent passes (95 % of HBM peak), so size 16 never becomes the default -- it is only recorded as available
-    // for the small-batch case (or forced by the test hook)
-    for (int nc = 1, idx = 0; nc <= 16; nc <<= 1, ++idx) {
-        if (forced && nc != forced) continue;
-        if (nc > n.W1) break;
-        const int Mmax = (n.W1 + nc - 1) / nc;
-        const size_t smem = td_smem_bytes(Mmax, n.Dp);
-        if (smem > (size_t)TD_SMEM_LIMIT) continue;
-        int ok = 0;
-        switch (n.G) {
-            case 1: ok = td_max_clusters<1>(nc, smem, Mmax); break;
-            case 2: ok = td_max_clusters<2>(nc, smem, Mmax); break;
-            case 4: ok = td_max_clusters<4>(nc, smem, Mmax); break;
-            case 8: ok = td_max_clusters<8>(nc, smem, Mmax); break;
-            case 16: ok = td_max_clusters<16>(nc, smem, Mmax); break;
-            default: ok = td_max_clusters<32>(nc, smem, Mmax); break;
-        }
-        if (ok > 0) {
-            c->td_nc_mask |= (unsigned)nc;
-            c->td_nc_cap[idx] = ok;
-            if (!smallest && (forced || nc <= 8)) smallest = nc;
-        }
-    }
-    return smallest;
+    SweepPlan p;
+    sweep_plan(c, c->maxB, forced, &p);
+    return p.NS;
 }
 
 // Geometry of the reversed right-image planes for the cost kernel (see k_sgbm_prefilter / k_sgbm_vsum).
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF)
 {
     const int PX = vs_compute_threads(n.G) / n.G;
-    const int NE = PX - 1 + n.Dp;                    // entries a CTA can touch
+    const int NE = PX - 1 + 8 * n.G;                 // entries a CTA can touch (== VsGeom<G>::NE)
     const int nv = (NE + 2 + 7) / 8;                 // == VsGeom<G>::NV
     const int K = W - PX - n.minX1 + n.minD;         // j0 = JOFF + K - xa must be a multiple of 8 (xa is)
     const int joff = PX + 8 + (((8 - ((PX + 8 + K) % 8)) % 8 + 8) % 8);
@@ -1303,7 +774,7 @@ void launch_sgbm(mvsv_ctx* c, int B)
         KernelTimer kt(c, KID_FILL);
         k_fill_i16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp_raw, npx, (int16_t)n.INV);
     } else {
-        const bool pad = n.D != n.Dp;
+        const bool pad = n.D != 8 * n.G;             // some lanes of a pixel's lane group hold no disparity
         switch (n.G) {
             case 1: if (pad) launch_sgbm_g<1, true>(c, B); else launch_sgbm_g<1, false>(c, B); break;
             case 2: if (pad) launch_sgbm_g<2, true>(c, B); else launch_sgbm_g<2, false>(c, B); break;

@@ -23,6 +23,8 @@ else:
     H, W = 1080, 1920
     p = dict(minDisp=0, numDisp=256, blockSize=5, disp12MaxDiff=1, preFilterCap=0, uniquenessRatio=10,
              speckleWindowSize=150, speckleRange=2, disparityMode=1, P1=200, P2=800)
+if os.environ.get("MVSV_W"):
+    W = int(os.environ["MVSV_W"])
 l, r, _ = synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=0)
 L = np.stack([l] * B)
 R = np.stack([r] * B)
