@@ -113,7 +113,7 @@ int main(int argc, char** argv)
     if (mvsv_set_sgbm_params(ctx, &p) != MVSV_OK) { std::fprintf(stderr, "%s\n", mvsv_last_error(ctx)); return 4; }
 
     // createDMapROIS (trgt/demo.cpp:87-113): the detectors see dMapRaw(cols >= numDisp/2)
-    const int pixelShift = p.numDisp / 2, cols = info.width - pixelShift, rows = info.height;
+    const int pixelShift = mvsv::dMapRoiOffset(p.numDisp, info.width), cols = info.width - pixelShift, rows = info.height;
     const float Q[16] = {1, 0, 0, -376.f, 0, 1, 0, -240.f, 0, 0, 0, 607.f, 0, 0, 1.f / 118.7f, 0};
     mvsv::MeanDisparityDetection m;
     mvsv::SamplepointDetection sd;

@@ -142,6 +142,16 @@ int mvsv_tm(mvsv_ctx* ctx, const uint8_t* left, size_t lstride, const uint8_t* r
  *   means : batch x num_rois float */
 int mvsv_download(mvsv_ctx* ctx, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride,
                   float* xyz, float* means);
+/* Pipelining inside one engine.  With two I/O slots (default: one) consecutive compute calls alternate between two
+ * sets of input / result buffers while sharing one set of cost volumes: the host->device copy of call k+1 runs on
+ * the copy stream while the kernels of call k execute, and mvsv_download_age(ctx, 1, ...) fetches the results of
+ * call k (age 1 = the call before the last one) on a download stream while the kernels of call k+1 execute.  The
+ * kernels themselves run in submission order on the ctx stream.  A slot's results must be downloaded before the
+ * call after next overwrites them.  No reference counterpart (the reference computes one pair per call on the
+ * CPU, src/disparity.cpp:6-10); mvsv_download == age 0. */
+int mvsv_set_io_slots(mvsv_ctx* ctx, int n);
+int mvsv_download_age(mvsv_ctx* ctx, int age, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride,
+                      float* xyz, float* means);
 /* Utility::calcMinMaxDisparity (src/utility.cpp:287-304) of the last computed maps as a GPU reduction: for every
  * frame the smallest and largest disparity value > 0, minmax[2*i], minmax[2*i+1]; (0, 0) when a map has none (the
  * reference dereferences an end iterator there).  Consumed by the PLY writer's grey ramp (src/ply.cpp:62-95). */

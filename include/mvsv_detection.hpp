@@ -98,6 +98,19 @@ struct Samplepoint {
     }
 };
 
+// pixelShift of createDMapROIS (trgt/demo.cpp:87-101): the consumers see dMapRaw(cols >= pixelShift).  numDisp / 2,
+// made even; the reference's adjustment for an odd half (`shift + (cols - shift % 8)`, operator precedence as written)
+// is kept as is.  Pass the result as x_offset to the detectors' init().
+inline int dMapRoiOffset(int numDisp, int cols)
+{
+    int pixelShift = numDisp / 2;
+    if (pixelShift % 2 == 1) {
+        pixelShift = pixelShift + 1;
+        if ((cols - pixelShift) % 8 != 0) pixelShift = pixelShift + (cols - pixelShift % 8);
+    }
+    return pixelShift;
+}
+
 // src/ObstacleDetection.cpp + inc/ObstacleDetection.h
 class ObstacleDetection {
 public:

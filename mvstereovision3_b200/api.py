@@ -19,7 +19,7 @@ ABI_SYMBOLS = (
     "mvsv_upload_rectify_maps", "mvsv_set_rectification", "mvsv_set_resize", "mvsv_reset_rectification", "mvsv_set_Q", "mvsv_set_mean_rois", "mvsv_compute",
     "mvsv_compute_device", "mvsv_tm", "mvsv_order_after", "mvsv_download", "mvsv_sync", "mvsv_get_info", "mvsv_stream", "mvsv_launch_count",
     "mvsv_host_alloc", "mvsv_host_free", "mvsv_debug_set_flags", "mvsv_debug_read",
-    "mvsv_download_minmax", "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
+    "mvsv_download_minmax", "mvsv_download_age", "mvsv_set_io_slots", "mvsv_timer_start", "mvsv_timer_stop", "mvsv_profile_enable", "mvsv_profile_read", "mvsv_kernel_name",
 )
 
 
@@ -76,6 +76,8 @@ def load_library():
     lib.mvsv_compute_device.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint]
     lib.mvsv_tm.argtypes = [vp, vp, sz, vp, sz, sz, ci, C.c_uint, vp, sz]
     lib.mvsv_download.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+    lib.mvsv_download_age.argtypes = [vp, ci, vp, sz, vp, vp, sz, vp, vp]
+    lib.mvsv_set_io_slots.argtypes = [vp, ci]
     lib.mvsv_sync.argtypes = [vp]
     lib.mvsv_order_after.argtypes = [vp, vp]
     lib.mvsv_download_minmax.argtypes = [vp, vp]
@@ -273,9 +275,15 @@ class Engine:
         if batch != i.last_batch:
             raise ValueError("download(%d): the last compute held %d stereo pairs" % (batch, i.last_batch))
 
-    def download(self, batch, disp=True, rect=False, xyz=False, means=False, out=None):
+    def set_io_slots(self, n):
+        """1 (default) or 2 sets of input/result buffers: with 2, compute k+1 may be submitted before the results of
+        compute k are fetched with download(..., age=1); copies and kernels then overlap inside this one engine."""
+        self._ck(self._lib.mvsv_set_io_slots(self._ctx, n))
+
+    def download(self, batch, disp=True, rect=False, xyz=False, means=False, out=None, age=0):
         i = self.info
-        self._check_batch(batch, i)
+        if age == 0:
+            self._check_batch(batch, i)
         H, W = i.height, i.width
         res = {}
         d = (out["disp"] if out and "disp" in out else np.empty((batch, H, W), np.int16)) if disp else None
@@ -283,7 +291,7 @@ class Engine:
         rr = np.empty((batch, H, W), np.uint8) if rect else None
         xz = np.empty((batch, H, W, 3), np.float32) if xyz else None
         mn = np.empty((batch, i.num_rois), np.float32) if means else None
-        self._ck(self._lib.mvsv_download(self._ctx, d.ctypes.data if disp else None, W * 2,
+        self._ck(self._lib.mvsv_download_age(self._ctx, age, d.ctypes.data if disp else None, W * 2,
                                          rl.ctypes.data if rect else None, rr.ctypes.data if rect else None, W,
                                          xz.ctypes.data if xyz else None, mn.ctypes.data if means else None))
         if disp:

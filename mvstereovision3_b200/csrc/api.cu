@@ -39,12 +39,28 @@ int fail(mvsv_ctx* c, int code, const std::string& msg)
     return code;
 }
 
+// the ctx-level rect / raw / disp / xyz / means pointers alias the I/O slot of the compute in progress
+void select_slot(mvsv_ctx* c, int k)
+{
+    c->cur = k;
+    mvsv_ctx::IoSlot& s = c->slot[k];
+    for (int i = 0; i < 2; ++i) { c->rect[i] = s.rect[i]; c->raw[i] = s.raw[i]; }
+    c->disp = s.disp; c->xyz = s.xyz; c->means = s.means;
+}
+
 void free_images(mvsv_ctx* c)
 {
-    for (int i = 0; i < 2; ++i) { dfree(c->rect[i]); dfree(c->bm_pre[i]); }
+    for (auto& s : c->slot) {
+        for (int i = 0; i < 2; ++i) dfree(s.rect[i]);
+        dfree(s.disp); dfree(s.xyz);
+        s.B = 0; s.stages = 0;
+    }
+    for (int i = 0; i < 2; ++i) { c->rect[i] = nullptr; dfree(c->bm_pre[i]); }
+    c->disp = nullptr; c->xyz = nullptr;
+    c->lastB = 0;
     dfree(c->recL);
-    dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->disp); dfree(c->labels); dfree(c->sizes);
-    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->xyz); dfree(c->minmax); dfree(c->tm_out);
+    dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->labels); dfree(c->sizes);
+    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->minmax); dfree(c->tm_out);
 }
 void free_sgbm_volumes(mvsv_ctx* c)
 {
@@ -62,20 +78,21 @@ int alloc_images(mvsv_ctx* c)
     const size_t B = (size_t)c->maxB, npx = B * c->H * c->W, nimg = B * c->H * c->pitch;
     // the connected-components labels of the speckle filter are int indices over the whole batch
     if (nimg >= ((size_t)1 << 31)) return fail(c, MVSV_ERR_UNSUPPORTED, "max_batch * height * width must stay below 2^31 pixels");
-    for (int i = 0; i < 2; ++i) {
-        MVSV_CK(c, cudaMalloc(&c->rect[i], nimg));
-        MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg + 64));      // the BM column-sum kernel reads whole aligned words
+    for (int k = 0; k < c->nslots; ++k) {
+        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->slot[k].rect[i], nimg));
+        MVSV_CK(c, cudaMalloc(&c->slot[k].disp, npx * sizeof(int16_t)));
+        MVSV_CK(c, cudaMemsetAsync(c->slot[k].disp, 0, npx * sizeof(int16_t), c->stream));
     }
+    for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->bm_pre[i], nimg + 64));   // the BM column-sum kernel reads whole aligned words
     MVSV_CK(c, cudaMalloc(&c->recL, npx * sizeof(uint2)));
     MVSV_CK(c, cudaMalloc(&c->d2, npx * sizeof(int)));
     MVSV_CK(c, cudaMalloc(&c->disp_raw, npx * sizeof(int16_t)));
     MVSV_CK(c, cudaMalloc(&c->disp_med, npx * sizeof(int16_t)));
-    MVSV_CK(c, cudaMalloc(&c->disp, npx * sizeof(int16_t)));
     MVSV_CK(c, cudaMalloc(&c->labels, npx * sizeof(int)));
     MVSV_CK(c, cudaMalloc(&c->sizes, npx * sizeof(int)));
     MVSV_CK(c, cudaMalloc(&c->bm_tex, npx * sizeof(uint16_t)));
     MVSV_CK(c, cudaMalloc(&c->bm_tex2, npx * sizeof(int)));
-    MVSV_CK(c, cudaMemsetAsync(c->disp, 0, npx * sizeof(int16_t), c->stream));
+    select_slot(c, 0);
     return MVSV_OK;
 }
 
@@ -221,11 +238,15 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
     if ((stages & MVSV_STAGE_XYZ) && !c->has_Q) return fail(c, MVSV_ERR_STATE, "mvsv_set_Q not called");
     if ((stages & MVSV_STAGE_MEANS) && (c->nrois < 1 || !c->rois || !c->means))
         return fail(c, MVSV_ERR_STATE, "no mean-disparity ROIs (mvsv_set_mean_rois; a geometry change drops them)");
-    // host inputs: the copies wait for this engine's previous work (which may still read the input buffers), the
+    if ((stages & MVSV_STAGE_RECTIFY) && (!c->has_maps[0] || !c->has_maps[1]))
+        return fail(c, MVSV_ERR_STATE, "rectify maps missing (mvsv_upload_rectify_maps)");
+    // next I/O slot; its previous results must have been downloaded by now (mvsv_set_io_slots)
+    select_slot(c, (c->cur + 1) % c->nslots);
+    mvsv_ctx::IoSlot& slot = c->slot[c->cur];
+    // host inputs: the copies wait for the slot's previous compute (which may still read the input buffers), the
     // kernels wait for the copies
-    if (!device_src) MVSV_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
+    if (!device_src) MVSV_CK(c, cudaStreamWaitEvent(c->copy_stream, slot.done, 0));
     if (stages & MVSV_STAGE_RECTIFY) {
-        if (!c->has_maps[0] || !c->has_maps[1]) return fail(c, MVSV_ERR_STATE, "rectify maps missing (mvsv_upload_rectify_maps)");
         if (lstride < (size_t)c->fw || rstride < (size_t)c->fw) return fail(c, MVSV_ERR_INVALID, "stride smaller than frame width");
         rc = upload_images(c, c->raw[0], c->raw_pitch, left, lstride, frame_stride, c->fw, c->fh, batch, device_src);
         if (rc) return rc;
@@ -256,14 +277,55 @@ int run(mvsv_ctx* c, const uint8_t* left, size_t lstride, const uint8_t* right, 
         launch_bm(c, batch);
     }
     if (stages & MVSV_STAGE_XYZ) {
-        if (!c->xyz) MVSV_CK(c, cudaMalloc(&c->xyz, (size_t)c->maxB * c->H * c->W * 3 * sizeof(float)));
+        if (!slot.xyz) {
+            MVSV_CK(c, cudaMalloc(&slot.xyz, (size_t)c->maxB * c->H * c->W * 3 * sizeof(float)));
+            c->xyz = slot.xyz;
+        }
         launch_xyz(c, batch);
     }
     if (stages & MVSV_STAGE_MEANS) launch_means(c, batch);
     MVSV_CK(c, cudaGetLastError());
+    MVSV_CK(c, cudaEventRecord(slot.done, c->stream));
     MVSV_CK(c, cudaEventRecord(c->ev_done, c->stream));
+    slot.B = batch; slot.stages = stages;
     c->lastB = batch;
     c->last_stages = stages;
+    return MVSV_OK;
+}
+
+// Copies the results a compute left in I/O slot `k` to the host on the download stream (so that it overlaps kernels
+// submitted later) and waits for them.
+int download_slot(mvsv_ctx* c, int k, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride, float* xyz,
+                  float* means)
+{
+    mvsv_ctx::IoSlot& s = c->slot[k];
+    const int B = s.B;
+    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
+    cudaStream_t st = c->dl_stream;
+    MVSV_CK(c, cudaStreamWaitEvent(st, s.done, 0));
+    if (disp) {
+        if (dstride < (size_t)c->W * 2) return fail(c, MVSV_ERR_INVALID, "disparity stride too small");
+        if (dstride == (size_t)c->W * 2)
+            MVSV_CK(c, cudaMemcpyAsync(disp, s.disp, (size_t)c->W * 2 * c->H * B, cudaMemcpyDeviceToHost, st));
+        else
+            MVSV_CK(c, cudaMemcpy2DAsync(disp, dstride, s.disp, (size_t)c->W * 2, (size_t)c->W * 2, (size_t)c->H * B,
+                                         cudaMemcpyDeviceToHost, st));
+    }
+    uint8_t* r[2] = {rectL, rectR};
+    for (int i = 0; i < 2; ++i)
+        if (r[i]) {
+            if (rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "rectified stride too small");
+            MVSV_CK(c, cudaMemcpy2DAsync(r[i], rstride, s.rect[i], c->pitch, (size_t)c->W, (size_t)c->H * B, cudaMemcpyDeviceToHost, st));
+        }
+    if (xyz) {
+        if (!s.xyz || !(s.stages & MVSV_STAGE_XYZ)) return fail(c, MVSV_ERR_STATE, "XYZ stage was not computed");
+        MVSV_CK(c, cudaMemcpyAsync(xyz, s.xyz, (size_t)B * c->H * c->W * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (means) {
+        if (!s.means || !(s.stages & MVSV_STAGE_MEANS)) return fail(c, MVSV_ERR_STATE, "MEANS stage was not computed");
+        MVSV_CK(c, cudaMemcpyAsync(means, s.means, (size_t)B * c->nrois * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    MVSV_CK(c, cudaStreamSynchronize(st));
     return MVSV_OK;
 }
 
@@ -310,6 +372,9 @@ int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv
     }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& sl : c->slot)
+        if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (cudaEvent_t* ev : {&c->ev_h2d, &c->ev_done, &c->ev_order})
         if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = sgbm_configure_kernels()) != cudaSuccess) return bail(e, "cudaFuncSetAttribute");
@@ -324,12 +389,18 @@ void mvsv_destroy(mvsv_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->dl_stream) cudaStreamSynchronize(c->dl_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_images(c);
+    for (auto& sl : c->slot) {
+        for (int i = 0; i < 2; ++i) dfree(sl.raw[i]);
+        dfree(sl.means);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     free_sgbm_volumes(c);
     free_bm_volumes(c);
-    for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->raw[i]); dfree(c->crop[i]); }
-    dfree(c->rois); dfree(c->means);
+    for (int i = 0; i < 2; ++i) { dfree(c->map_xy[i]); dfree(c->crop[i]); }
+    dfree(c->rois);
     for (auto& b : c->brackets) { cudaEventDestroy(b.a); cudaEventDestroy(b.b); }
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
@@ -337,6 +408,7 @@ void mvsv_destroy(mvsv_ctx* c)
     for (cudaEvent_t ev : {c->ev_h2d, c->ev_done, c->ev_order})
         if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -385,7 +457,9 @@ static int resize_rectified(mvsv_ctx* c, int W, int H)
     if (!rc && c->has_bm) rc = normalise_bm(c, &c->bm_raw, &bm);
     if (rc) { c->W = oldW; c->H = oldH; return rc; }
     // mean-disparity ROIs are coordinates of the old map: drop them (run() asks for new ones)
-    dfree(c->rois); dfree(c->means);
+    dfree(c->rois);
+    for (auto& sl : c->slot) dfree(sl.means);
+    c->means = nullptr;
     c->nrois = 0;
     rc = alloc_images(c);
     if (rc) return rc;
@@ -444,10 +518,11 @@ static int prepare_maps(mvsv_ctx* c, int cam, int roi_x, int roi_y, int roi_w, i
     MVSV_CK(c, cudaMalloc(&c->map_xy[cam], (size_t)roi_w * roi_h * sizeof(int2)));
     int rc = apply_geometry(c);
     if (rc) return rc;
-    if (!c->raw[0]) {
-        c->raw_pitch = round_up((size_t)c->fw, 16);
-        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&c->raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
-    }
+    c->raw_pitch = round_up((size_t)c->fw, 16);
+    for (int k = 0; k < c->nslots; ++k)
+        for (int i = 0; i < 2; ++i)
+            if (!c->slot[k].raw[i]) MVSV_CK(c, cudaMalloc(&c->slot[k].raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
+    select_slot(c, c->cur);
     return MVSV_OK;
 }
 
@@ -588,11 +663,14 @@ int mvsv_set_mean_rois(mvsv_ctx* c, const int* xywh, int n)
             return fail(c, MVSV_ERR_INVALID, "ROI outside the disparity map");
     }
     MVSV_CK(c, cudaStreamSynchronize(c->stream));
-    dfree(c->rois); dfree(c->means);
+    dfree(c->rois);
+    for (auto& sl : c->slot) dfree(sl.means);
+    c->means = nullptr;
     c->nrois = n;
     if (n == 0) return MVSV_OK;
     MVSV_CK(c, cudaMalloc(&c->rois, (size_t)n * 4 * sizeof(int)));
-    MVSV_CK(c, cudaMalloc(&c->means, (size_t)n * c->maxB * sizeof(float)));
+    for (int k = 0; k < c->nslots; ++k) MVSV_CK(c, cudaMalloc(&c->slot[k].means, (size_t)n * c->maxB * sizeof(float)));
+    select_slot(c, c->cur);
     MVSV_CK(c, cudaMemcpy(c->rois, xywh, (size_t)n * 4 * sizeof(int), cudaMemcpyHostToDevice));
     return MVSV_OK;
 }
@@ -612,35 +690,48 @@ int mvsv_compute_device(mvsv_ctx* c, const uint8_t* dleft, size_t lstride, const
 int mvsv_download(mvsv_ctx* c, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride, float* xyz,
                   float* means)
 {
+    return mvsv_download_age(c, 0, disp, dstride, rectL, rectR, rstride, xyz, means);
+}
+
+int mvsv_download_age(mvsv_ctx* c, int age, int16_t* disp, size_t dstride, uint8_t* rectL, uint8_t* rectR, size_t rstride,
+                      float* xyz, float* means)
+{
     if (!c) return MVSV_ERR_INVALID;
     int rc = bind(c);
     if (rc) return rc;
-    const int B = c->lastB;
-    if (B < 1) return fail(c, MVSV_ERR_STATE, "nothing computed yet");
-    if (disp) {
-        if (dstride < (size_t)c->W * 2) return fail(c, MVSV_ERR_INVALID, "disparity stride too small");
-        if (dstride == (size_t)c->W * 2)
-            MVSV_CK(c, cudaMemcpyAsync(disp, c->disp, (size_t)c->W * 2 * c->H * B, cudaMemcpyDeviceToHost, c->stream));
-        else
-            MVSV_CK(c, cudaMemcpy2DAsync(disp, dstride, c->disp, (size_t)c->W * 2, (size_t)c->W * 2, (size_t)c->H * B,
-                                         cudaMemcpyDeviceToHost, c->stream));
-    }
-    uint8_t* r[2] = {rectL, rectR};
-    for (int i = 0; i < 2; ++i)
-        if (r[i]) {
-            if (rstride < (size_t)c->W) return fail(c, MVSV_ERR_INVALID, "rectified stride too small");
-            MVSV_CK(c, cudaMemcpy2DAsync(r[i], rstride, c->rect[i], c->pitch, (size_t)c->W, (size_t)c->H * B,
-                                         cudaMemcpyDeviceToHost, c->stream));
-        }
-    if (xyz) {
-        if (!c->xyz || !(c->last_stages & MVSV_STAGE_XYZ)) return fail(c, MVSV_ERR_STATE, "XYZ stage was not computed");
-        MVSV_CK(c, cudaMemcpyAsync(xyz, c->xyz, (size_t)B * c->H * c->W * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    }
-    if (means) {
-        if (!c->means || !(c->last_stages & MVSV_STAGE_MEANS)) return fail(c, MVSV_ERR_STATE, "MEANS stage was not computed");
-        MVSV_CK(c, cudaMemcpyAsync(means, c->means, (size_t)B * c->nrois * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    }
+    if (age < 0 || age >= c->nslots) return fail(c, MVSV_ERR_INVALID, "age must be below the number of I/O slots");
+    return download_slot(c, (c->cur + c->nslots - age) % c->nslots, disp, dstride, rectL, rectR, rstride, xyz, means);
+}
+
+int mvsv_set_io_slots(mvsv_ctx* c, int n)
+{
+    if (!c) return MVSV_ERR_INVALID;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (n != 1 && n != 2) return fail(c, MVSV_ERR_INVALID, "1 or 2 I/O slots");
+    if (n == c->nslots) return MVSV_OK;
     MVSV_CK(c, cudaStreamSynchronize(c->stream));
+    MVSV_CK(c, cudaStreamSynchronize(c->copy_stream));
+    const bool hadRaw = c->slot[0].raw[0] != nullptr;
+    const bool hadMeans = c->slot[0].means != nullptr;
+    if (n < c->nslots) {
+        mvsv_ctx::IoSlot& s = c->slot[1];
+        for (int i = 0; i < 2; ++i) { dfree(s.rect[i]); dfree(s.raw[i]); }
+        dfree(s.disp); dfree(s.xyz); dfree(s.means);
+        s.B = 0; s.stages = 0;
+        c->nslots = n;
+        select_slot(c, 0);
+        return MVSV_OK;
+    }
+    c->nslots = n;
+    mvsv_ctx::IoSlot& s = c->slot[1];
+    const size_t npx = (size_t)c->maxB * c->H * c->W, nimg = (size_t)c->maxB * c->H * c->pitch;
+    for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&s.rect[i], nimg));
+    MVSV_CK(c, cudaMalloc(&s.disp, npx * sizeof(int16_t)));
+    MVSV_CK(c, cudaMemsetAsync(s.disp, 0, npx * sizeof(int16_t), c->stream));
+    if (hadRaw)
+        for (int i = 0; i < 2; ++i) MVSV_CK(c, cudaMalloc(&s.raw[i], (size_t)c->maxB * c->fh * c->raw_pitch));
+    if (hadMeans) MVSV_CK(c, cudaMalloc(&s.means, (size_t)c->nrois * c->maxB * sizeof(float)));
     return MVSV_OK;
 }
 

@@ -68,8 +68,25 @@ struct mvsv_ctx {
     uint8_t* crop[2] = {nullptr, nullptr};    // [B][roi_h][crop_pitch]: remap output when a resize follows
     size_t crop_pitch = 0;
 
-    uint8_t* rect[2] = {nullptr, nullptr};    // [B][H][pitch]
+    uint8_t* rect[2] = {nullptr, nullptr};    // [B][H][pitch] -- of the current I/O slot (see below)
     size_t pitch = 0;
+
+    // I/O slots (mvsv_set_io_slots): the buffers a compute call reads its inputs into and leaves its results in exist
+    // once or twice; with two, the host->device copy of the next batch and the device->host copy of the previous
+    // one overlap the kernels of the current batch inside ONE engine (one set of cost volumes).  rect / raw / disp /
+    // xyz / means above and below always alias the slot of the compute in progress.
+    int nslots = 1, cur = 0;
+    struct IoSlot {
+        uint8_t* rect[2] = {nullptr, nullptr};
+        uint8_t* raw[2] = {nullptr, nullptr};
+        int16_t* disp = nullptr;
+        float* xyz = nullptr;
+        float* means = nullptr;
+        cudaEvent_t done = nullptr;           // all kernels of the slot's last compute have finished
+        int B = 0;
+        unsigned stages = 0;
+    } slot[2];
+    cudaStream_t dl_stream = nullptr;         // device->host result copies
 
     bool has_sgbm = false, has_bm = false;
     mvsv_sgbm_params sgbm_raw{};

@@ -287,13 +287,15 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
             const bool recvPx = DIR ? lastPx : firstPx, sendPx = DIR ? firstPx : lastPx;
             const bool nbStripR = DIR ? hasR : hasL, nbStripS = DIR ? hasL : hasR;   // strip we receive from / send to
             unsigned mm;
+            // Pace against the neighbouring warp on every row -- also on a frame's first row, which needs no data from
+            // it: the slot ring only has room for a drift of one row per warp boundary.
+            if (DIR ? (w < wl) : (w > 0)) {
+                const int* nb = prog + (DIR ? w + 1 : w - 1);
+                while (ld_acquire_cta(nb) < t) {}
+            }
             if (firstRow) {
                 reset_path<NR, G, PAD>(L, mm, q, jpad);
             } else {
-                if (DIR ? (w < wl) : (w > 0)) {
-                    const int* nb = prog + (DIR ? w + 1 : w - 1);
-                    while (ld_acquire_cta(nb) < t) {}
-                }
                 if (recvPx) {
                     // the strip's border pixel: predecessor is off the cost domain (state 0) or in the next strip (record)
                     if (nbStripR) {
@@ -453,7 +455,11 @@ void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p)
     sweep_layout(n.D, &G, &NR);
     if (G * 2 * NR != n.Dp) return;                   // volumes are laid out with another pixel stride
     const int capThreads = SW_MAX_THREADS / 32 * 32;
-    double best = -1.0;
+    // Time model (measured on B200, profiles/r02_sweep_row_time.txt): a CTA's row takes about c0 + c1 * warps -- a
+    // latency floor plus the warps' share of the SM -- and a batch takes waves * H rows, waves = ceil(B / NF).
+    // Fewer, wider strips amortise the floor; more strips keep the frames of a small batch in one wave.
+    const double c0 = 1.1, c1 = 0.2;
+    double best = 1e300;
     for (int NS = 1; NS <= std::min(n.W1, c->num_sms); ++NS) {
         if (forcedNS > 0 && NS != forcedNS) continue;
         const int Mmax = (n.W1 + NS - 1) / NS;
@@ -462,12 +468,9 @@ void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p)
         const size_t smem = sweep_smem_bytes(NR, G, Mmax, nthr);
         if (smem > (size_t)SW_SMEM_LIMIT) continue;
         const int NF = std::min(B, c->num_sms / NS);
-        // score: lanes doing useful work over the whole GPU, per wave of frames
         const int waves = (B + NF - 1) / NF;
-        const double laneEff = (double)n.W1 * G / ((double)NS * nthr);
-        const double score = (double)B / waves * NS * laneEff * nthr / (double)(c->num_sms * capThreads)
-                             - 1e-4 * NS;           // ties: fewer strips (less halo traffic)
-        if (score > best) { best = score; p->NS = NS; p->NF = NF; p->Mmax = Mmax; p->threads = nthr; p->smem = smem; }
+        const double cost = waves * (c0 + c1 * (nthr / 32)) + 1e-6 * NS;   // ties: fewer strips (less border traffic)
+        if (cost < best) { best = cost; p->NS = NS; p->NF = NF; p->Mmax = Mmax; p->threads = nthr; p->smem = smem; }
     }
     p->G = G; p->NR = NR;
 }

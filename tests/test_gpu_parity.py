@@ -58,8 +58,8 @@ def test_sgbm_stages_vs_oracle(oracle, golden, case):
 @pytest.mark.parametrize("nc", [1, 2, 4, 8, 0xff])
 @pytest.mark.parametrize("ci", [0, 1, 3, 7])
 def test_fused_sweep_cluster_sizes(oracle, ci, nc):
-    """The fused previous-row sweep (thread-block cluster, DSMEM halo exchange) at every cluster size, and the
-    independent-pass fallback (0xff), give the same bits as the oracle (MODE_SGBM and MODE_HH, padded D)."""
+    """The fused previous-row sweep (csrc/sweep.cu) with 1, 2, 4 and 8 column strips per frame, and the
+    independent-pass fallback (0xff), give the same bits as the oracle (MODE_SGBM and MODE_HH, D = 64, 32, 48, 128)."""
     name, p, H, W = cases.SGBM_CASES[ci]
     l, r = cases.sgbm_inputs(name, p, H, W, "noise")
     with api.Engine(W, H, max_batch=2) as e:
@@ -206,8 +206,9 @@ CFG4 = cases.sgbm_params(numDisp=256, blockSize=5, P1=200, P2=800, disp12MaxDiff
 CFG5 = cases.sgbm_params(numDisp=256, blockSize=5, P1=200, P2=800)
 
 
-@pytest.mark.parametrize("p,H,W,B", [(CFG2, 480, 752, 4), (CFG2_SHIPPED, 480, 752, 2), (CFG4, 1080, 1920, 1)],
-                         ids=["cfg2_752x480_d64", "sgbm_yml_d128", "cfg4_1080p_d256_hh"])
+@pytest.mark.parametrize("p,H,W,B", [(CFG2, 480, 752, 4), (CFG2_SHIPPED, 480, 752, 2), (CFG4, 1080, 1920, 1),
+                                     (CFG5, 2160, 3840, 1)],
+                         ids=["cfg2_752x480_d64", "sgbm_yml_d128", "cfg4_1080p_d256_hh", "cfg5_4k_d256"])
 def test_full_size_vs_cv2(p, H, W, B):
     cv2 = _cv2()
     ls, rs = [], []
@@ -353,10 +354,10 @@ def test_cpp_frame_loop_demo(tmp_path):
 @pytest.mark.parametrize("H", [1, 2, 3, 4, 7])
 @pytest.mark.parametrize("nc", [2, 4])
 def test_fused_sweep_degenerate_strips(oracle, H, nc):
-    """Halo hand-off corner cases: frames of 1..7 rows (fewer rows than halo slots) and column strips of one or two
-    pixels (a strip's first pixel is also its last), MODE_HH so that both sweeps run."""
+    """Border hand-off corner cases: frames of 1..7 rows (fewer rows than border-record slots) and column strips of
+    one or two pixels (a strip's first pixel is also its last), MODE_HH so that both sweeps run."""
     p = cases.sgbm_params(numDisp=16, blockSize=3, P1=7, P2=40, uniquenessRatio=5, mode=1)
-    W = 16 + 5                                   # W1 = 5 -> strips of 1 or 2 columns at cluster size 4
+    W = 16 + 5                                   # W1 = 5 -> strips of 1 or 2 columns with 4 strips
     l, r = synth.random_pair(H, W, seed=90 + H)
     with api.Engine(W, H) as e:
         e.set_sgbm_params(**gpu_params(p))
@@ -394,10 +395,77 @@ def test_pipelined_engines_order_after(oracle):
         check("batch %d" % k, got[k], want[k])
 
 
+def test_io_slots_pipeline_in_one_engine(oracle):
+    """mvsv_set_io_slots(2): compute k+1 is submitted before the results of compute k are fetched (age 1); the
+    copies overlap the kernels inside ONE engine and every batch still equals the oracle (bench.py's e2e loop)."""
+    p = cases.sgbm_params(minDisp=1, numDisp=32, blockSize=5, P1=20, P2=90, uniquenessRatio=5, speckleWindowSize=30, speckleRange=2)
+    H, W, B = 60, 200, 6
+    batches = []
+    for k in range(5):
+        ls, rs = zip(*[synth.random_pair(H, W, seed=100 * k + b) for b in range(B)])
+        batches.append((np.stack(ls), np.stack(rs)))
+    want = [np.stack([oracle.sgbm(L[b], R[b], p) for b in range(B)]) for L, R in batches]
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.set_Q(cases.Q_REFERENCE)
+        e.set_mean_rois([(40, 5, 50, 40), (100, 10, 20, 20)])
+        e.set_io_slots(2)
+        got, means = [None] * len(batches), [None] * len(batches)
+        stages = api.STAGE_SGBM | api.STAGE_MEANS
+        e.compute(batches[0][0], batches[0][1], stages)
+        for k in range(1, len(batches)):
+            e.compute(batches[k][0], batches[k][1], stages)
+            r = e.download(B, means=True, age=1)
+            got[k - 1], means[k - 1] = r["disp"], r["means"]
+        r = e.download(B, means=True)
+        got[-1], means[-1] = r["disp"], r["means"]
+        with pytest.raises(api.MvsvError):
+            e.download(B, age=2)
+        e.set_io_slots(1)
+        e.compute(batches[2][0], batches[2][1], api.STAGE_SGBM)
+        check("back to one slot", e.download(B)["disp"], want[2])
+    for k in range(len(batches)):
+        check("batch %d" % k, got[k], want[k])
+        for b in range(B):
+            m = np.array([oracle.mean(want[k][b], roi) for roi in [(40, 5, 50, 40), (100, 10, 20, 20)]], np.float32)
+            np.testing.assert_array_equal(means[k][b], m)
+
+
+def test_mean_rois_dropped_on_geometry_change(oracle):
+    """ROIs are coordinates of the current map: a geometry change drops them, MEANS then fails with MVSV_ERR_STATE
+    until they are set again (and never launches with stale ROIs or a freed result buffer)."""
+    H, W = 96, 140
+    img, img2 = synth.random_pair(H, W, seed=5)
+    mx, my = cases.warp_maps(H, W, 1)
+    p = cases.sgbm_params(numDisp=16, blockSize=5)
+    with api.Engine(W, H, max_batch=1) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.set_mean_rois([(100, 60, 30, 30)])
+        e.compute(img, img2, api.STAGE_SGBM | api.STAGE_MEANS)
+        e.download(1, means=True)
+        roi = (4, 2, W - 40, H - 30)                      # the old ROI now lies outside the map
+        e.upload_rectify_maps(0, mx, my, roi)
+        e.upload_rectify_maps(1, mx, my, roi)
+        assert e.info.num_rois == 0
+        with pytest.raises(api.MvsvError) as ex:
+            e.compute(img, img2, api.STAGE_RECTIFY | api.STAGE_SGBM | api.STAGE_MEANS)
+        assert ex.value.code == -4
+        e.set_mean_rois([(10, 10, 30, 30)])
+        e.compute(img, img2, api.STAGE_RECTIFY | api.STAGE_SGBM | api.STAGE_MEANS)
+        out = e.download(1, means=True)
+        rl, rr = oracle.remap(img, mx, my, roi), oracle.remap(img2, mx, my, roi)
+        disp = oracle.sgbm(rl, rr, p)
+        check("disp", out["disp"][0], disp)
+        np.testing.assert_array_equal(out["means"][0], np.array([oracle.mean(disp, (10, 10, 30, 30))], np.float32))
+        with pytest.raises(ValueError):
+            e.download(2)                                  # more frames than the last compute held
+
+
 @pytest.mark.parametrize("nc", [1, 2, 4, 8])
 def test_halo_handoff_soak(oracle, nc):
-    """Determinism soak of the st.async + mbarrier halo hand-off: 100 x 24 small MODE_HH frames (two sweeps each)
-    at every cluster size, each result identical to the oracle."""
+    """Determinism soak of the strip-border hand-off of the fused sweep (tagged records through L2, neighbouring
+    warps paced by shared-memory progress counters): 100 x 24 small MODE_HH frames (two sweeps each) at 1, 2, 4 and
+    8 strips per frame, each result identical to the oracle."""
     p = cases.sgbm_params(minDisp=1, numDisp=32, blockSize=5, P1=20, P2=90, uniquenessRatio=5, disp12MaxDiff=1,
                           speckleWindowSize=30, speckleRange=2, mode=1)
     H, W, B = 37, 171, 24
@@ -412,3 +480,25 @@ def test_halo_handoff_soak(oracle, nc):
             e.compute(L, R, api.STAGE_SGBM)
             got = e.download(B)["disp"]
             assert np.array_equal(got, want), "cluster %d, iteration %d: %d pixels differ" % (nc, it, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("D,nc,B", [(32, 8, 60), (128, 16, 30), (256, 37, 9)])
+def test_sweep_walks_several_frames_per_cta(oracle, D, nc, B):
+    """More frames than frame slots (B > floor(148 / strips)): every CTA of the persistent sweep walks several frames,
+    warps and strips drift across the frame boundaries, and all frames (MODE_HH: two sweeps) still equal the oracle --
+    the frame-boundary case of the border hand-off, at one, two and four lanes per pixel."""
+    p = cases.sgbm_params(minDisp=0, numDisp=D, blockSize=3, P1=20, P2=90, uniquenessRatio=5, disp12MaxDiff=1, mode=1)
+    H, W = 9, D + 150
+    ls, rs = zip(*[synth.random_pair(H, W, seed=300 + s) for s in range(6)])
+    L, R = np.stack([ls[b % 6] for b in range(B)]), np.stack([rs[b % 6] for b in range(B)])
+    want = [oracle.sgbm(ls[b], rs[b], p) for b in range(6)]
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        e.debug_set_flags(nc << 8)
+        assert e.info.sgbm_td_cluster == nc and B > 148 // nc
+        for it in range(20):
+            e.compute(L, R, api.STAGE_SGBM)
+            got = e.download(B)["disp"]
+            for b in range(B):
+                assert np.array_equal(got[b], want[b % 6]), "iteration %d frame %d: %d pixels differ" % (
+                    it, b, int((got[b] != want[b % 6]).sum()))

@@ -105,3 +105,21 @@ def test_cpp_mirror_compiles_as_cxx11(tmp_path):
     """include/mvsv_disparity.hpp (the C++ mirror of reference inc/disparity.h) builds with -std=c++11 like the
     reference (Makefile:7) and links against libmvsv.so only."""
     assert os.path.exists(_build_shim_demo(tmp_path))
+
+
+def test_cpp_dmap_roi_offset_matches_reference_arithmetic(tmp_path):
+    """mvsv::dMapRoiOffset (include/mvsv_detection.hpp) == createDMapROIS' pixelShift (reference trgt/demo.cpp:87-96),
+    including the odd-half branch, for every numDisp the contract allows and a few widths."""
+    import subprocess
+    src = tmp_path / "off.cpp"
+    src.write_text('#include "mvsv_detection.hpp"\n#include <cstdio>\n#include <cstdlib>\n'
+                   'int main(int c, char** v) { for (int i = 1; i + 1 < c; i += 2) '
+                   'std::printf("%d\\n", mvsv::dMapRoiOffset(std::atoi(v[i]), std::atoi(v[i + 1]))); return 0; }\n')
+    exe = str(tmp_path / "off")
+    subprocess.check_call(["g++", "-std=c++11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe])
+    pairs = [(d, w) for d in range(8, 257, 8) for w in (752, 376, 1920, 3840, 201)]
+    args = [str(x) for p in pairs for x in p]
+    got = [int(x) for x in subprocess.check_output([exe] + args).decode().split()]
+    assert got == [api.dmap_roi_offset(d, w) for d, w in pairs]
+    # numDisp / 2 whenever that is even -- all a reachable configuration produces with numDisp % 16 == 0
+    assert all(api.dmap_roi_offset(d, 752) == d // 2 for d in range(16, 257, 16))
