@@ -788,6 +788,7 @@ int mvsv_get_info(const mvsv_ctx* c, mvsv_info* info)
     }
     info->num_rois = c->nrois; info->device = c->device; info->sgbm_td_cluster = c->has_sgbm ? c->td_nc : 0;
     info->last_batch = c->lastB;
+    info->sgbm_s8 = c->last_s8 ? 1 : 0;
     return MVSV_OK;
 }
 
@@ -878,9 +879,15 @@ long long mvsv_debug_read(mvsv_ctx* c, int which, void* host, size_t cap)
     const size_t img16 = (size_t)B * c->H * c->W * 2;
     switch (which) {
         case 0: src = c->C; bytes = vol; break;
-        case 1: src = c->S; bytes = vol; break;
+        case 1:
+            // with S kept as bytes (S8) the complete 16-bit S only exists when the test hook asked the last scan to
+            // store it (debug flag bit 0); it then lives in the VS volume, which is dead by that time
+            if (c->last_s8 && !(c->debug_flags & 1)) return fail(c, MVSV_ERR_STATE, "S is held as bytes: set debug flag bit 0 before the compute");
+            src = c->last_s8 ? c->VS : c->S; bytes = vol; break;
         case 2: src = c->disp_raw; bytes = img16; break;
-        case 3: src = c->VS; bytes = vol; break;
+        case 3:
+            if (c->last_s8 && (c->debug_flags & 1)) return fail(c, MVSV_ERR_STATE, "the VS volume was reused for the final S (debug flag bit 0)");
+            src = c->VS; bytes = vol; break;
         case 4: src = (c->has_sgbm && c->sg.speckleWin > 0) ? c->disp_med : c->disp; bytes = img16; break;
         case 5: src = c->bm_pre[0]; bytes = (size_t)B * c->H * c->pitch; break;
         case 6: src = c->bm_pre[1]; bytes = (size_t)B * c->H * c->pitch; break;

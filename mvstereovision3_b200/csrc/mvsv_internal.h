@@ -48,7 +48,8 @@ struct mvsv_ctx {
     int lastB = 0;
     unsigned last_stages = 0;
     unsigned long long launches = 0;
-    unsigned debug_flags = 0;   // bit0: h2 pass stores the final S volume (test hook)
+    unsigned debug_flags = 0;   // bit0: h2 pass stores the final S volume (test hook); bit1: never use the byte form of S
+    bool last_s8 = false;       // the last SGBM compute kept S as bytes (S8)
     bool prof = false;
     std::vector<ProfBracket> brackets;      // pending (unread) timed launches
     std::vector<cudaEvent_t> ev_free;       // recycled events
@@ -168,7 +169,8 @@ struct SweepPlan { int NS = 0, NF = 0, Mmax = 0, threads = 0, G = 0, NR = 0; siz
 void sweep_layout(int D, int* G, int* NR);
 void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p);
 size_t sweep_scratch_bytes(const mvsv_ctx* c);
-cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp);
+bool sweep_s8_ok(const mvsv_ctx* c, const SweepPlan& p);
+cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp, bool s8);
 int sgbm_choose_td_cluster(mvsv_ctx* c);
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);
 

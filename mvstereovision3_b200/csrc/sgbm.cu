@@ -12,6 +12,10 @@
 // packed 16x2 (VIADD.16x2 / VIMNMX.U16x2 / VIMNMX3 / VIADDMNMX -- the DPX path on sm_100a).
 #include "mvsv_internal.h"
 
+#include <algorithm>
+#include <cstdlib>
+#include <functional>
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -373,6 +377,9 @@ struct AggArgs {
     int16_t* disp; int* d2;
     int minD, minX1, maxX1, INV, uniq, d12;
     int storeS;
+    // S8: the S volume holds, per cell, the byte (sum of the paths so far) - (paths so far) * C (see sweep.cu)
+    uint16_t* Sdbg;             // where the final S goes when the test hook asks for it in S8 mode (the dead VS volume)
+    unsigned nprevPk, kclampPk; // S8: paths accumulated before the last scan, and ceil(32767 / that), both packed x2
 };
 
 // The row scans stream their operands through a per-lane shared-memory ring filled by cp.async (LDGSTS): the
@@ -382,8 +389,9 @@ constexpr int H1_PFD = 8;
 constexpr int HPF = 2;         // k_sgbm_h2_wta is issue-bound: it keeps a cheap 2-step register prefetch instead
 
 
-// K3a: horizontal box sum (VS -> C) fused with the left-to-right path r=(-1,0).  Writes C and S = L.
-template <int G, bool PAD>
+// K3a: horizontal box sum (VS -> C) fused with the left-to-right path r=(-1,0).  Writes C and S = L
+// (S8: the bytes L - C, one per disparity).
+template <int G, bool PAD, bool S8>
 __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
 {
     // a pixel's stride in the volumes is a.Dp <= 8*G: lanes beyond it hold padding only and never touch memory
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
     const uint16_t* __restrict__ vs = a.VS + rowBase;
     uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
+    uint8_t* __restrict__ sp8 = reinterpret_cast<uint8_t*>(a.S) + rowBase;      // S8: one byte per cell, same indexing
 
     // Stream element t = VS[clamp(t - SW2)], t >= 0.  The window of step xi is t in [xi, xi + bs): it gains
     // t = xi + bs and loses t = xi.  Ring slot of t is t mod R with R = bs + PFD, so the element fetched at step
@@ -434,7 +443,13 @@ __global__ void __launch_bounds__(128) k_sgbm_h1(AggArgs a)
         sgm_step<G, PAD>(L, mm, hs, a.P1P1, a.P2P2, q, padLane);
         if (active) {
             st128(cp + xi * DP, hs);
-            st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
+            if (S8) {
+                // L - C is in [0, P2] for every disparity (no borrow between the halves): keep the low bytes
+                const unsigned e0 = L[0] - hs.x, e1 = L[1] - hs.y, e2 = L[2] - hs.z, e3 = L[3] - hs.w;
+                *reinterpret_cast<uint2*>(sp8 + xi * DP) = make_uint2(__byte_perm(e0, e1, 0x6420), __byte_perm(e2, e3, 0x6420));
+            } else {
+                st128(sp + xi * DP, make_uint4(L[0], L[1], L[2], L[3]));
+            }
         }
         hs.x += nx.x - od.x; hs.y += nx.y - od.y; hs.z += nx.z - od.z; hs.w += nx.w - od.w;
     }
@@ -506,7 +521,7 @@ __device__ __forceinline__ int div_trunc_small(int n, int d)
     return n < 0 ? -qq : qq;
 }
 
-template <int G, bool PAD>
+template <int G, bool PAD, bool S8>
 __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
 {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,6 +537,8 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     const size_t rowBase = (size_t)row * W1 * Dp + (mem ? q * 8 : 0);
     const uint16_t* __restrict__ cp = a.C + rowBase;
     uint16_t* __restrict__ sp = a.S + rowBase;
+    const uint8_t* __restrict__ sp8 = reinterpret_cast<const uint8_t*>(a.S) + rowBase;
+    uint16_t* __restrict__ sdbg = (S8 ? a.Sdbg : a.S) + rowBase;       // test hook: where the final S is stored
     int16_t* __restrict__ drow = a.disp + (size_t)row * a.W;
     int* __restrict__ d2row = a.d2 + (size_t)row * a.W;
     // disp2 entry of right-image column j: (minS << 16) | (W1-1-xi) of the best left pixel xi that maps to j.  The
@@ -561,12 +578,24 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     auto step = [&](const uint4& Cq, const uint4& Sq, int xi) {
         sgm_step<G, PAD>(L, mm, Cq, a.P1P1, a.P2P2, q, padLane);
         unsigned Sf[4];
-        Sf[0] = __viaddmin_u16x2(Sq.x, L[0], MVSV_PK_MAX);
-        Sf[1] = __viaddmin_u16x2(Sq.y, L[1], MVSV_PK_MAX);
-        Sf[2] = __viaddmin_u16x2(Sq.z, L[2], MVSV_PK_MAX);
-        Sf[3] = __viaddmin_u16x2(Sq.w, L[3], MVSV_PK_MAX);
+        uint4 Si = Sq;
+        if (S8) {
+            // sum of the n paths before this one = n * C + byte.  With c' = min(C, ceil(32767 / n)) the product
+            // n * c' + byte fits 16 bits and is >= 32767 exactly when the true sum is: saturate afterwards.
+            const unsigned b0 = __byte_perm(Sq.x, 0, 0x4140), b1 = __byte_perm(Sq.x, 0, 0x4342);
+            const unsigned b2 = __byte_perm(Sq.y, 0, 0x4140), b3 = __byte_perm(Sq.y, 0, 0x4342);
+            const unsigned n1 = a.nprevPk & 0xffffu;
+            Si.x = __vminu2(__vminu2(Cq.x, a.kclampPk) * n1 + b0, MVSV_PK_MAX);
+            Si.y = __vminu2(__vminu2(Cq.y, a.kclampPk) * n1 + b1, MVSV_PK_MAX);
+            Si.z = __vminu2(__vminu2(Cq.z, a.kclampPk) * n1 + b2, MVSV_PK_MAX);
+            Si.w = __vminu2(__vminu2(Cq.w, a.kclampPk) * n1 + b3, MVSV_PK_MAX);
+        }
+        Sf[0] = __viaddmin_u16x2(Si.x, L[0], MVSV_PK_MAX);
+        Sf[1] = __viaddmin_u16x2(Si.y, L[1], MVSV_PK_MAX);
+        Sf[2] = __viaddmin_u16x2(Si.z, L[2], MVSV_PK_MAX);
+        Sf[3] = __viaddmin_u16x2(Si.w, L[3], MVSV_PK_MAX);
         if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
-        if (a.storeS && active && mem) st128(sp + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
+        if (a.storeS && active && mem) st128(sdbg + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
         // ---- first argmin via (S << 16 | k) keys
         unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
                            min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
@@ -603,7 +632,13 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
 #pragma unroll
         for (int k = 0; k < HPF; ++k) {
             const int xn = max(xfirst - k, 0);
-            Cd[k] = ld128(cp + xn * Dp); Sd[k] = ld128(sp + xn * Dp);
+            Cd[k] = ld128(cp + xn * Dp);
+            if (S8) {
+                const uint2 e = *reinterpret_cast<const uint2*>(sp8 + xn * Dp);
+                Sd[k] = make_uint4(e.x, e.y, 0u, 0u);
+            } else {
+                Sd[k] = ld128(sp + xn * Dp);
+            }
         }
     };
     auto run = [&](const uint4 (&Cs)[HPF], const uint4 (&Ss)[HPF], int xfirst) {
@@ -656,6 +691,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->recL, c->plR,
                                               planeStrideR, c->vsRP, c->vsJOFF);
     }
+    std::function<void(int, int)> launch_vsum;
     {
         constexpr int PX = VsGeom<G>::PX;
         VsArgs a;
@@ -672,15 +708,19 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         int bands = 1;
         while (bands < 8 && (long long)gx * B * (bands * 2) <= c->num_sms && c->H / (bands * 2) >= 4 * bs) bands *= 2;
         a.bandRows = (c->H + bands - 1) / bands;
-        dim3 grd(gx, B, (c->H + a.bandRows - 1) / a.bandRows);
-        KernelTimer kt(c, KID_SGBM_VSUM);
-        if (bands > 1) {
-            if (r8) k_sgbm_vsum<G, true, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
-            else k_sgbm_vsum<G, false, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
-        } else {
-            if (r8) k_sgbm_vsum<G, true, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
-            else k_sgbm_vsum<G, false, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(a);
-        }
+        launch_vsum = [=](int f0, int nb) {
+            VsArgs v = a;
+            v.recL += (size_t)f0 * c->H * c->W; v.plR += (size_t)f0 * c->H * c->vsRP; v.VS += (size_t)f0 * c->H * n.W1 * n.Dp;
+            dim3 grd(gx, nb, (c->H + v.bandRows - 1) / v.bandRows);
+            KernelTimer kt(c, KID_SGBM_VSUM);
+            if (bands > 1) {
+                if (r8) k_sgbm_vsum<G, true, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+                else k_sgbm_vsum<G, false, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+            } else {
+                if (r8) k_sgbm_vsum<G, true, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+                else k_sgbm_vsum<G, false, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+            }
+        };
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
@@ -691,16 +731,31 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     const int TPB = 128;
     const long long rowThreads = (long long)B * c->H * G, colThreads = (long long)B * n.W1 * G;
     const unsigned rowBlocks = (unsigned)((rowThreads + TPB - 1) / TPB), colBlocks = (unsigned)((colThreads + TPB - 1) / TPB);
-    { KernelTimer kt(c, KID_SGBM_H1); k_sgbm_h1<G, PAD><<<rowBlocks, TPB, (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16, st>>>(a); }
     // the three previous-row paths: fused strip sweep (csrc/sweep.cu); independent passes only when it cannot run
     SweepPlan plan;
     {
         const int forced = (int)((c->debug_flags >> 8) & 0xff);
         if (forced != 0xff) sweep_plan(c, B, forced, &plan);
     }
+    // S8: every path cost is C + e with 0 <= e <= P2, so while npaths * P2 <= 255 the S volume only carries the byte
+    // sum of the e's (half the traffic of S in all three aggregation kernels); needs the sweep's lane layout
+    const bool s8 = plan.NS > 0 && sweep_s8_ok(c, plan) && !(c->debug_flags & 2);
+    c->last_s8 = s8;
+    a.Sdbg = c->VS;
+    {
+        const unsigned nprev = (unsigned)(n.npaths - 1), kcl = (32767u + nprev - 1) / nprev;
+        a.nprevPk = nprev * 0x10001u; a.kclampPk = kcl * 0x10001u;
+    }
+    launch_vsum(0, B);
+    {
+        KernelTimer kt(c, KID_SGBM_H1);
+        const size_t sm = (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16;
+        if (s8) k_sgbm_h1<G, PAD, true><<<rowBlocks, TPB, sm, st>>>(a);
+        else k_sgbm_h1<G, PAD, false><<<rowBlocks, TPB, sm, st>>>(a);
+    }
     auto vdirs = [&](int bottomUp) {
         if (plan.NS > 0) {
-            launch_sweep(c, B, plan, bottomUp);
+            launch_sweep(c, B, plan, bottomUp, s8);
         } else {
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, -1, bottomUp); }
             { KernelTimer kt(c, KID_SGBM_VDIR); k_sgbm_vdir<G, PAD><<<colBlocks, TPB, 0, st>>>(a, 0, bottomUp); }
@@ -709,7 +764,11 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     };
     vdirs(0);
     if (n.mode == 1) vdirs(1);
-    { KernelTimer kt(c, KID_SGBM_H2_WTA); k_sgbm_h2_wta<G, PAD><<<rowBlocks, TPB, 0, st>>>(a); }
+    {
+        KernelTimer kt(c, KID_SGBM_H2_WTA);
+        if (s8) k_sgbm_h2_wta<G, PAD, true><<<rowBlocks, TPB, 0, st>>>(a);
+        else k_sgbm_h2_wta<G, PAD, false><<<rowBlocks, TPB, 0, st>>>(a);
+    }
 }
 
 template <int G>
@@ -723,9 +782,13 @@ cudaError_t cfg_vsum()
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_h1<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_h1<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_sgbm_h1<G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
 }

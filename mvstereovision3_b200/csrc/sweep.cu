@@ -38,6 +38,7 @@
 #include "mvsv_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace {
@@ -51,7 +52,9 @@ struct SweepArgs {
     int H, W1, D, Dp, B;
     int NS, NF, Mmax;            // strips per frame, frames in flight, widest strip
     int bottomUp;
-    int fast;                    // 3 * (bs^2 * (2*ftzero+63) + P2) <= 65535: the paths of a row are summed without saturation
+    int dsm;                     // the NS strips of a frame form a thread-block cluster: border records go through
+                                 // distributed shared memory instead of global memory
+    int mode;                    // 0 saturating adds, 1 plain adds of the row's paths, 2 S as bytes (see k_sweep)
     unsigned one;                // always 1 (see path_step)
     unsigned P1P1, P2P2;
     uint16_t* halo;              // [NF][NS][2][NSLOT][Dp + 8] u16: tagged border records (dir 0: for the strip to the right)
@@ -85,6 +88,27 @@ __device__ __forceinline__ uint4 ld_relaxed128(const void* p)
 __device__ __forceinline__ void st_relaxed128(void* p, const uint4& v)
 {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// distributed shared memory (the strips of a frame launched as one thread-block cluster)
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned cta)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_dsm128(unsigned raddr, const uint4& v)
+{
+    asm volatile("st.relaxed.cluster.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_dsm128(const unsigned* p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.cluster.shared::cta.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 constexpr unsigned TAGMASK = 0x80008000u;
 // border records per boundary and direction: with the role-based path order a sender can be three rows ahead of the
@@ -173,12 +197,19 @@ __host__ __device__ constexpr int sweep_stages(int NR) { return NR >= 20 ? 1 : N
 // lanes fall into eight different bank groups
 __host__ __device__ constexpr int sweep_lbw(int NR) { return ((NR / 4) | 1) * 4; }
 
-// FAST: 3 * (largest possible path cost) <= 65535, so the three paths of a row are summed with plain adds and
-// saturated once when they are added to S (host-checked; otherwise every add saturates).
-template <int NR, int G, bool PAD, bool FAST>
+// MODE 0: every add into S saturates.  MODE 1: 3 * (largest possible path cost) <= 65535 (host-checked), so the three
+// paths of a row are summed with plain adds and saturated once when they are added to S.  MODE 2 ("S8"): as MODE 1,
+// and the S volume holds one BYTE per cell: (sum of the paths so far) - (paths so far) * C, which is the sum of the
+// paths' excesses L - C, each in [0, P2]; the host checks npaths * P2 <= 255.  The sweep then adds the byte
+// (L1 + L2 + L3 - 3 C) and moves half as many S bytes.
+template <int NR, int G, bool PAD, int MODE>
 __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
 {
+    constexpr bool FAST = MODE >= 1, S8 = MODE == 2;
     constexpr int NRC = NR / 4, LBW = sweep_lbw(NR), NSTG = sweep_stages(NR);
+    // S blocks: NR registers of packed u16 (LBW words apart), or NR / 2 registers of bytes (S8; NR % 8 == 0)
+    constexpr int NRS = S8 ? NR / 2 : NR, NRCS = NRS / 4, LBWS = S8 ? sweep_lbw(NRS) : LBW;
+    static_assert(!S8 || NR % 8 == 0, "the byte form of S needs whole 16-byte chunks per lane");
     extern __shared__ __align__(16) unsigned smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nthr = blockDim.x, nw = nthr >> 5;
     const int q = tid % G;
@@ -186,29 +217,38 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
     const int x0 = (int)(((long long)a.W1 * s) / a.NS), x1 = (int)(((long long)a.W1 * (s + 1)) / a.NS);
     const int M = x1 - x0;
     const int R = a.Mmax + nw;                       // ring of skewed state slots (nw spare: warps drift by <= 1 row each)
-    // layout (words): st1[R*G][LBW] | st2[R*G][LBW] | stgC[NSTG][nthr][LBW] | stgS[NSTG][nthr][LBW] | m1[R] | m2[R] |
+    // layout (words): st1[R*G][LBW] | st2[R*G][LBW] | stgC[NSTG][nthr][LBW] | stgS[NSTG][nthr][LBWS] | m1[R] | m2[R] |
     //                 prog1[nw] | prog2[nw]
     unsigned* const st1 = smem;
     unsigned* const st2 = st1 + (size_t)R * G * LBW;
     unsigned* const stgC = st2 + (size_t)R * G * LBW;
     unsigned* const stgS = stgC + (size_t)NSTG * nthr * LBW;
-    unsigned* const m1 = stgS + (size_t)NSTG * nthr * LBW;
+    unsigned* const m1 = stgS + (size_t)NSTG * nthr * LBWS;
     unsigned* const m2 = m1 + R;
     int* const prog1 = reinterpret_cast<int*>(m2 + R);
     int* const prog2 = prog1 + nw;
+    // border records received through distributed shared memory: rec[dir][NSLOT][HBW] words, 16-byte aligned
+    const int HBW = a.Dp / 2 + 4;
+    unsigned* const rec = smem + (((size_t)(prog2 + nw - reinterpret_cast<int*>(smem)) + 3) & ~(size_t)3);
+    const bool dsm = a.dsm != 0;
 
     if (tid < nw) { prog1[tid] = 0; prog2[tid] = 0; }
-    __syncthreads();
+    if (dsm) {
+        for (int i = tid; i < 2 * NSLOT * HBW; i += nthr) rec[i] = 0u;          // tag 0: nothing received yet
+        cluster_sync_all();                       // every strip of the frame is resident and cleared before any remote store
+    } else {
+        __syncthreads();
+    }
 
     const int lxr = tid / G;                          // pixel of this lane inside the strip
     const bool act = lxr < M;
     const int lx = act ? lxr : M - 1;
     const int nact = min(max(M * G - w * 32, 0), 32); // active lanes of this warp
-    if (nact == 0) return;                            // (only possible for trailing warps of a narrower strip)
+    // (nact == 0 is only possible for trailing warps of a narrower strip: they skip the row loop)
     const int wl = (M * G - 1) >> 5;                  // warp holding the strip's last pixel
     const int jpad = PAD ? (a.D - (G - 1) * 2 * NR) / 2 : NR;
     const int nfr = (a.B - fs + a.NF - 1) / a.NF;     // frames this CTA walks
-    const int T = nfr * a.H;
+    const int T = nact > 0 ? nfr * a.H : 0;
     const bool hasL = s > 0, hasR = s + 1 < a.NS;
     const bool firstPx = act && lxr == 0, lastPx = act && lxr == M - 1;
     const int HB = a.Dp + 8;                          // border record: Dp path costs + packed minimum (padded to 16 bytes)
@@ -223,7 +263,7 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
     // the warp's span of a row: nact lane blocks, contiguous in global memory.  Chunk c = i*32 + lane of the span
     // belongs to lane c / NRC, position c % NRC.
     const size_t rowElems = (size_t)a.W1 * a.Dp;
-    const size_t warpOff = (size_t)(x0 + (w * 32) / G) * a.Dp + (size_t)lane * 8;
+    const size_t warpOff = (size_t)(x0 + (w * 32) / G) * a.Dp;       // in cells; the lane's 16-byte chunk is added below
     const int nchunks = nact * NRC;
     // element offset of the warp's span in the row that is k rows ahead of (fi, yi), k < H
     auto row_off = [&](int fi, int yi, int k) -> size_t {
@@ -238,20 +278,38 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         const int c = i * 32 + lane, o = c / NRC, j = c - o * NRC;
         cdst[i] = c < nchunks ? (w * 32 + o) * LBW + j * 4 : -1;
     }
-    auto issue = [&](const uint16_t* vol, unsigned* stg, int t, size_t off) {
+    int sdst[NRCS];                                   // the same for the S blocks (S8: half as many chunks)
+#pragma unroll
+    for (int i = 0; i < NRCS; ++i) {
+        const int c = i * 32 + lane, o = c / NRCS, j = c - o * NRCS;
+        sdst[i] = c < nact * NRCS ? (w * 32 + o) * LBWS + j * 4 : -1;
+    }
+    const char* const Cbytes = reinterpret_cast<const char*>(a.C) + (size_t)lane * 16;
+    char* const Sbytes = reinterpret_cast<char*>(a.S) + (size_t)lane * 16;
+    auto issueC = [&](int t, size_t cellOff) {
         if (t < T) {
-            const uint16_t* src = vol + off;
-            unsigned* dst = stg + (size_t)(t % NSTG) * nthr * LBW;
+            const char* src = Cbytes + cellOff * 2;
+            unsigned* dst = stgC + (size_t)(t % NSTG) * nthr * LBW;
 #pragma unroll
             for (int i = 0; i < NRC; ++i)
-                if (cdst[i] >= 0) cp_async16(smem_u32(dst + cdst[i]), src + (size_t)i * 256);
+                if (cdst[i] >= 0) cp_async16(smem_u32(dst + cdst[i]), src + (size_t)i * 512);
+        }
+        cp_async_commit();
+    };
+    auto issueS = [&](int t, size_t cellOff) {
+        if (t < T) {
+            const char* src = Sbytes + cellOff * (S8 ? 1 : 2);
+            unsigned* dst = stgS + (size_t)(t % NSTG) * nthr * LBWS;
+#pragma unroll
+            for (int i = 0; i < NRCS; ++i)
+                if (sdst[i] >= 0) cp_async16(smem_u32(dst + sdst[i]), src + (size_t)i * 512);
         }
         cp_async_commit();
     };
 #pragma unroll
-    for (int k = 0; k < NSTG; ++k) issue(a.C, stgC, k, row_off(k / a.H, k % a.H, 0));
+    for (int k = 0; k < NSTG; ++k) issueC(k, row_off(k / a.H, k % a.H, 0));
 #pragma unroll
-    for (int k = 0; k + 1 < NSTG; ++k) issue(a.S, stgS, k, row_off(k / a.H, k % a.H, 0));
+    for (int k = 0; k + 1 < NSTG; ++k) issueS(k, row_off(k / a.H, k % a.H, 0));
     cp_async_wait<2 * (NSTG - 1)>();                  // C of row 0 has landed
     __syncwarp();
 
@@ -267,7 +325,7 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         unsigned Cc[NR];
         lds_block<NR>(Cc, stgC + ((size_t)st * nthr + tid) * LBW);
         __syncwarp();
-        issue(a.C, stgC, t + NSTG, row_off(fi + NSTG / a.H, yi, NSTG % a.H));
+        issueC(t + NSTG, row_off(fi + NSTG / a.H, yi, NSTG % a.H));
 
         unsigned Ss[NR];                              // sum of the three paths of this row
         // tag of the records received in this row / sent for the next one: 4 bits in the free top bits of the first
@@ -303,15 +361,16 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
                         // 8-byte half carries this row's tag (one L2 round trip once the record is there)
                         const uint16_t* hb = (DIR ? recvR : recvL) + (size_t)(t % NSLOT) * HB;
                         const uint16_t* hp = hb + (size_t)q * 2 * NR;
+                        const unsigned* rb = rec + (size_t)(DIR * NSLOT + t % NSLOT) * HBW;     // the same record in shared memory
                         unsigned bad;
                         uint4 mrec = make_uint4(tagRx, tagRy, 0u, 0u);
                         do {
 #pragma unroll
                             for (int j = 0; j < NR; j += 4) {
-                                const uint4 v = ld_relaxed128(hp + 2 * j);
+                                const uint4 v = dsm ? ld_dsm128(rb + q * NR + j) : ld_relaxed128(hp + 2 * j);
                                 L[j] = v.x; L[j + 1] = v.y; L[j + 2] = v.z; L[j + 3] = v.w;
                             }
-                            if (q == 0) mrec = ld_relaxed128(hb + a.Dp);
+                            if (q == 0) mrec = dsm ? ld_dsm128(rb + a.Dp / 2) : ld_relaxed128(hb + a.Dp);
                             bad = ((mrec.x & TAGMASK) ^ tagRx) | ((mrec.y & TAGMASK) ^ tagRy);
 #pragma unroll
                             for (int j = 0; j < NR; j += 2) bad |= ((L[j] & TAGMASK) ^ tagRx) | ((L[j + 1] & TAGMASK) ^ tagRy);
@@ -335,11 +394,20 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
                 sts_block<NR>(slot, L);
                 if (q == 0) mArr[sidx] = mm;
                 if (sendPx && nbStripS && !lastRow) {
-                    uint16_t* hp = (DIR ? sendL : sendR) + (size_t)((t + 1) % NSLOT) * HB;
+                    if (dsm) {
+                        // the neighbour strip is CTA s -/+ 1 of this cluster; its rec[DIR] takes what we send in direction DIR
+                        const unsigned rb = mapa_u32(smem_u32(rec + (size_t)(DIR * NSLOT + (t + 1) % NSLOT) * HBW), (unsigned)(DIR ? s - 1 : s + 1));
 #pragma unroll
-                    for (int j = 0; j < NR; j += 4)
-                        st_relaxed128(hp + (size_t)q * 2 * NR + 2 * j, make_uint4(L[j] | tagSx, L[j + 1] | tagSy, L[j + 2] | tagSx, L[j + 3] | tagSy));
-                    if (q == 0) st_relaxed128(hp + a.Dp, make_uint4(mm | tagSx, tagSy, tagSx, tagSy));
+                        for (int j = 0; j < NR; j += 4)
+                            st_dsm128(rb + (unsigned)(q * NR + j) * 4u, make_uint4(L[j] | tagSx, L[j + 1] | tagSy, L[j + 2] | tagSx, L[j + 3] | tagSy));
+                        if (q == 0) st_dsm128(rb + (unsigned)(a.Dp / 2) * 4u, make_uint4(mm | tagSx, tagSy, tagSx, tagSy));
+                    } else {
+                        uint16_t* hp = (DIR ? sendL : sendR) + (size_t)((t + 1) % NSLOT) * HB;
+#pragma unroll
+                        for (int j = 0; j < NR; j += 4)
+                            st_relaxed128(hp + (size_t)q * 2 * NR + 2 * j, make_uint4(L[j] | tagSx, L[j + 1] | tagSy, L[j + 2] | tagSx, L[j + 3] | tagSy));
+                        if (q == 0) st_relaxed128(hp + a.Dp, make_uint4(mm | tagSx, tagSy, tagSx, tagSy));
+                    }
                 }
             }
             __syncwarp();
@@ -349,7 +417,7 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         // ---- diagonal from x-1 first: it feeds the warp / strip to the right
         diag(std::integral_constant<int, 0>(), Ss);
         // ---- S of row t + NSTG - 1 into the stage whose write-back (row t - 1) has been read out
-        issue(a.S, stgS, t + NSTG - 1, row_off(fi + (NSTG - 1) / a.H, yi, (NSTG - 1) % a.H));
+        issueS(t + NSTG - 1, row_off(fi + (NSTG - 1) / a.H, yi, (NSTG - 1) % a.H));
         // ---- vertical path: state in registers
         if (firstRow) reset_path<NR, G, PAD>(Lv, mv, q, jpad);
         path_step<NR, G, PAD>(Lv, mv, Cc, a.P1P1, a.P2P2, one, q, jpad);
@@ -364,57 +432,87 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         }
         // ---- S += the three paths, in place in shared memory, then coalesced write-back of the warp's span
         {
-            unsigned* const stage = stgS + (size_t)st * nthr * LBW;
-            unsigned* const sb = stage + (size_t)tid * LBW;
+            unsigned* const stage = stgS + (size_t)st * nthr * LBWS;
+            unsigned* const sb = stage + (size_t)tid * LBWS;
             cp_async_wait<2 * (NSTG - 1)>();          // S of this row (and C of the next) have landed
             __syncwarp();
-            unsigned Sin[NR];
-            lds_block<NR>(Sin, sb);
+            unsigned Sin[NRS];
+            lds_block<NRS>(Sin, sb);
+            if (S8) {
+                // bytes of L1 + L2 + L3 - 3 C (each path's excess is in [0, P2], the byte sums stay below 256)
 #pragma unroll
-            for (int j = 0; j < NR; ++j)      // FAST: the plain sum of three paths may exceed 0x7fff (but not 0xffff)
-                Ss[j] = __viaddmin_u16x2(FAST ? __vminu2(Ss[j], MVSV_PK_MAX) : Ss[j], Sin[j], MVSV_PK_MAX);
-            sts_block<NR>(sb, Ss);
+                for (int j = 0; j < NR; ++j) Ss[j] -= 3u * Cc[j];
+#pragma unroll
+                for (int j = 0; j < NRS; ++j) Sin[j] += __byte_perm(Ss[2 * j], Ss[2 * j + 1], 0x6420);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j)  // FAST: the plain sum of three paths may exceed 0x7fff (but not 0xffff)
+                    Sin[j] = __viaddmin_u16x2(FAST ? __vminu2(Ss[j], MVSV_PK_MAX) : Ss[j], Sin[j], MVSV_PK_MAX);
+            }
+            sts_block<NRS>(sb, Sin);
             __syncwarp();
-            uint16_t* dst = a.S + row_off(fi, yi, 0);
+            char* dst = Sbytes + row_off(fi, yi, 0) * (S8 ? 1 : 2);
 #pragma unroll
-            for (int i = 0; i < NRC; ++i)
-                if (cdst[i] >= 0) *reinterpret_cast<uint4*>(dst + (size_t)i * 256) = *reinterpret_cast<const uint4*>(stage + cdst[i]);
+            for (int i = 0; i < NRCS; ++i)
+                if (sdst[i] >= 0) *reinterpret_cast<uint4*>(dst + (size_t)i * 512) = *reinterpret_cast<const uint4*>(stage + sdst[i]);
         }
         if (--s1 < 0) s1 += R;
         if (++s2 >= R) s2 -= R;
         if (++yi == a.H) { yi = 0; ++fi; }
     }
     cp_async_wait<0>();
+    if (dsm) cluster_sync_all();                  // no strip may exit while a neighbour can still store into its shared memory
 }
 
 size_t sweep_smem_bytes(int NR, int G, int Mmax, int nthr)
 {
     const int LBW = sweep_lbw(NR), NSTG = sweep_stages(NR), nw = nthr / 32, R = Mmax + nw;
-    const size_t words = (size_t)2 * R * G * LBW + (size_t)2 * NSTG * nthr * LBW + 2 * R + 2 * nw;
+    size_t words = (size_t)2 * R * G * LBW + (size_t)2 * NSTG * nthr * LBW + 2 * R + 2 * nw;
+    words = ((words + 3) & ~(size_t)3) + (size_t)2 * NSLOT * (G * NR + 4);      // + border records (cluster hand-off)
     return words * 4;
 }
 
-template <int NR, int G, bool PAD, bool FAST>
-cudaError_t launch_fast(const SweepArgs& a, int nthr, size_t smem, cudaStream_t st)
+template <int NR, int G, bool PAD, int MODE>
+cudaError_t launch_fast(const SweepArgs& a0, int nthr, size_t smem, cudaStream_t st)
 {
+    SweepArgs a = a0;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep<NR, G, PAD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<NR, G, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.NS * a.NF, 1, 1); cfg.blockDim = dim3(nthr, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;      // all CTAs co-resident: they wait on one another
+    if (a.dsm) {
+        // the strips of a frame are one thread-block cluster (co-scheduled by the hardware); frames are independent
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = a.NS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    } else {
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;  // all CTAs co-resident: they wait on one another
+    }
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_sweep<NR, G, PAD, FAST>, a);
+    if (a.dsm) {
+        // frames in flight = clusters that can be resident at once (a GPC holds a whole number of clusters)
+        int nmax = 0;
+        if (cudaOccupancyMaxActiveClusters(&nmax, k_sweep<NR, G, PAD, MODE>, &cfg) != cudaSuccess || nmax < 1) {
+            cudaGetLastError();
+            nmax = a.NF;
+        }
+        a.NF = std::min(a.NF, nmax);
+        cfg.gridDim = dim3(a.NS * a.NF, 1, 1);
+    }
+    return cudaLaunchKernelEx(&cfg, k_sweep<NR, G, PAD, MODE>, a);
 }
 
 template <int NR, int G, bool PAD>
 cudaError_t launch_inst(const SweepArgs& a, int nthr, size_t smem, cudaStream_t st)
 {
-    return a.fast ? launch_fast<NR, G, PAD, true>(a, nthr, smem, st) : launch_fast<NR, G, PAD, false>(a, nthr, smem, st);
+    if constexpr (NR % 8 == 0) {
+        if (a.mode == 2) return launch_fast<NR, G, PAD, 2>(a, nthr, smem, st);
+    }
+    return a.mode >= 1 ? launch_fast<NR, G, PAD, 1>(a, nthr, smem, st) : launch_fast<NR, G, PAD, 0>(a, nthr, smem, st);
 }
 
 template <int G, bool PAD>
@@ -481,19 +579,31 @@ size_t sweep_scratch_bytes(const mvsv_ctx* c)
     return (size_t)c->num_sms * 2 * NSLOT * (256 + 8) * sizeof(uint16_t);
 }
 
-cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp)
+// 3 * (largest possible path cost) <= 65535: the three paths of a row can be summed in 16 bits without saturation
+static bool sweep_fast_ok(const SgbmNorm& n)
+{
+    const long long bs = 2 * n.SH2 + 1, lmax = bs * bs * (2 * n.ftzero + 63) + n.P2;
+    return 3 * lmax <= 65535;
+}
+
+// S as bytes: all npaths excesses (each <= P2) fit a byte, plain 16-bit row sums, whole 16-byte chunks per lane
+bool sweep_s8_ok(const mvsv_ctx* c, const SweepPlan& p)
+{
+    const SgbmNorm& n = c->sg;
+    return p.NS > 0 && p.NR % 8 == 0 && sweep_fast_ok(n) && (long long)n.npaths * n.P2 <= 255;
+}
+
+cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp, bool s8)
 {
     const SgbmNorm& n = c->sg;
     SweepArgs a;
     a.C = c->C; a.S = c->S; a.H = c->H; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.B = B;
     a.NS = p.NS; a.NF = p.NF; a.Mmax = p.Mmax; a.bottomUp = bottomUp;
+    a.dsm = (p.NS >= 2 && p.NS <= 8 && !getenv("MVSV_NO_DSM")) ? 1 : 0;
     a.P1P1 = ((unsigned)n.P1 & 0xffffu) * 0x10001u; a.P2P2 = ((unsigned)n.P2 & 0xffffu) * 0x10001u;
     a.halo = c->sweep_halo;
     a.one = 1u;
-    {
-        const long long bs = 2 * n.SH2 + 1, lmax = bs * bs * (2 * n.ftzero + 63) + n.P2;   // largest possible path cost
-        a.fast = 3 * lmax <= 65535 ? 1 : 0;
-    }
+    a.mode = s8 ? 2 : (sweep_fast_ok(n) ? 1 : 0);
     // tag 0 everywhere: no record of an earlier launch can be mistaken for one of this launch
     cudaError_t e = cudaMemsetAsync(c->sweep_halo, 0, (size_t)p.NS * p.NF * 2 * NSLOT * (n.Dp + 8) * sizeof(uint16_t), c->stream);
     if (e != cudaSuccess) return e;

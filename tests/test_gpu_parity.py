@@ -502,3 +502,37 @@ def test_sweep_walks_several_frames_per_cta(oracle, D, nc, B):
             for b in range(B):
                 assert np.array_equal(got[b], want[b % 6]), "iteration %d frame %d: %d pixels differ" % (
                     it, b, int((got[b] != want[b % 6]).sum()))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(minDisp=1, numDisp=64, blockSize=13, speckleWindowSize=150, speckleRange=2),             # cfg 2 (P2 -> 5)
+    dict(numDisp=32, blockSize=5, P1=3, P2=30, mode=1, uniquenessRatio=10, disp12MaxDiff=1),      # MODE_HH, 8 * 30 <= 255
+    dict(numDisp=128, blockSize=9, P1=8, P2=51, uniquenessRatio=5),                               # two lanes per pixel
+    dict(numDisp=256, blockSize=3, P1=2, P2=31, mode=1),                                          # four lanes, MODE_HH
+    dict(numDisp=48, blockSize=7, P1=10, P2=50, preFilterCap=63),                                 # 24 registers per lane
+    dict(numDisp=16, blockSize=11, P1=1, P2=2, preFilterCap=100),                                 # costs near the int16 limit
+], ids=["cfg2", "hh_d32", "d128", "d256_hh", "d48", "d16_wide"])
+def test_byte_form_of_S_equals_16bit_form(oracle, kw):
+    """When npaths * P2 <= 255 the aggregated volume is kept as one byte per cell (sum of the paths' excesses over
+    C); the same parameters with the byte form forced off (debug flag bit 1) and the oracle must give the same final S
+    volume and the same disparities."""
+    p = cases.sgbm_params(**kw)
+    H, W = 41, p["numDisp"] + 93
+    l, r = synth.random_pair(H, W, seed=11)
+    l2, r2, _ = synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=12)
+    L, R = np.stack([l, l2]), np.stack([r, r2])
+    res = {}
+    for flags in (1, 3):
+        with api.Engine(W, H, max_batch=2) as e:
+            e.set_sgbm_params(**gpu_params(p))
+            e.debug_set_flags(flags)
+            e.compute(L, R, api.STAGE_SGBM)
+            res[flags] = (e.download(2)["disp"], e.debug_read(1, 2), e.info.sgbm_s8)
+    bs = p["blockSize"] | 1
+    fast = 3 * (bs * bs * (2 * (max(p["preFilterCap"], 15) | 1) + 63) + max(p["P2"], 5)) <= 65535
+    assert res[1][2] == (1 if fast else 0) and res[3][2] == 0, "byte form expected by default (row sums fit 16 bits), 16-bit form when forced"
+    for b, (a_, b_) in enumerate(((l, r), (l2, r2))):
+        disp, Cv, Sv, rawv = oracle.sgbm(a_, b_, p, want_volumes=True, want_raw=True)
+        for flags in (1, 3):
+            check("S/%d/%d" % (flags, b), res[flags][1][b], Sv)
+            check("disp/%d/%d" % (flags, b), res[flags][0][b], disp)
