@@ -176,7 +176,7 @@ int normalise_bm(mvsv_ctx* c, const mvsv_bm_params* p, BmNorm* n)
     if ((long long)n->bs * n->bs * 2 * n->cap > 65535) return fail(c, MVSV_ERR_INVALID, "BM blockSize^2*2*cap > 65535 unsupported");
     int g = 2;
     while (g * 8 < n->D) g <<= 1;
-    n->G = g; n->Dp = g * 8; n->w2 = n->bs / 2;
+    n->G = g; n->Dp = n->D; n->w2 = n->bs / 2;      // lanes: next power of two; storage stride: numDisp itself
     n->lofs = n->D - 1; n->width1 = c->W - n->D + 1; n->FILT = -16;
     return MVSV_OK;
 }

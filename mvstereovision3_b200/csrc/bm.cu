@@ -12,69 +12,94 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-__global__ void k_bm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch, int W,
-                               int H, int cap, uint8_t* __restrict__ o0, uint8_t* __restrict__ o1)
+// Row-marching: a thread owns one column of BM_ROWS rows (an even count, so the row pairs of the reference's loop
+// never straddle two CTAs) and keeps the horizontal differences of the previous rows in registers.
+constexpr int BM_ROWS = 16;
+
+__global__ void __launch_bounds__(128)
+k_bm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch, int W, int H, int cap,
+               uint8_t* __restrict__ o0, uint8_t* __restrict__ o1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * BM_ROWS, y1 = min(y0 + BM_ROWS, H);
     const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
     if (x >= W) return;
     const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
-    uint8_t* out = (im ? o1 : o0) + ((size_t)f * H + y) * pitch + x;
-    int res = cap;
-    const bool lastOdd = (H & 1) && (y == H - 1);
-    if (x > 0 && x < W - 1 && !lastOdd) {
-        int ra, rb, rc;   // rows weighted 1, 2, 1
-        if ((y & 1) == 0) { ra = y > 0 ? y - 1 : y + 1; rb = y; rc = y + 1; }
-        else { const int yb = y - 1; ra = yb; rb = y; rc = (yb < H - 2) ? yb + 2 : yb; }
-        const uint8_t *pa = img + (size_t)ra * pitch, *pb = img + (size_t)rb * pitch, *pc = img + (size_t)rc * pitch;
-        const int v = ((int)pa[x + 1] - (int)pa[x - 1]) + 2 * ((int)pb[x + 1] - (int)pb[x - 1]) + ((int)pc[x + 1] - (int)pc[x - 1]);
-        res = v < -cap ? 0 : (v > cap ? 2 * cap : v + cap);
+    uint8_t* out = (im ? o1 : o0) + (size_t)f * H * pitch + x;
+    const bool inner = x > 0 && x < W - 1;
+    auto dx = [&](int r) -> int {                  // horizontal difference of row r (clamped into the image by the callers)
+        const uint8_t* p = img + (size_t)r * pitch + x;
+        return inner ? (int)p[1] - (int)p[-1] : 0;
+    };
+    auto clip = [&](int v) -> int { return v < -cap ? 0 : (v > cap ? 2 * cap : v + cap); };
+    // rows are processed in pairs (y, y + 1), y even: out[y] = d[r0] + 2 d[y] + d[y+1] with r0 = y-1 (y+1 at the top),
+    // out[y+1] = d[y] + 2 d[y+1] + d[r3] with r3 = y+2 (y at the bottom); an odd last row is the constant `cap`
+    for (int y = y0; y < y1; y += 2) {
+        if (y + 1 >= H) { out[(size_t)y * pitch] = (uint8_t)cap; break; }
+        const int d0 = dx(y > 0 ? y - 1 : y + 1), d1 = dx(y), d2 = dx(y + 1), d3 = dx(y < H - 2 ? y + 2 : y);
+        out[(size_t)y * pitch] = (uint8_t)(inner ? clip(d0 + 2 * d1 + d2) : cap);
+        out[(size_t)(y + 1) * pitch] = (uint8_t)(inner ? clip(d1 + 2 * d2 + d3) : cap);
     }
-    *out = (uint8_t)res;
 }
 
-// texture: separable window sum of |L - cap|
-__global__ void k_bm_tex_col(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap,
-                             uint16_t* __restrict__ tc)
+// texture: separable window sum of |L - cap|; the column pass slides down BM_ROWS rows per thread
+__global__ void __launch_bounds__(128)
+k_bm_tex_col(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap, uint16_t* __restrict__ tc)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + w2;
-    if (x >= W || y >= H - w2) return;
-    const uint8_t* p = preL + (size_t)blockIdx.z * H * pitch;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ya = blockIdx.y * BM_ROWS + w2, yb = min(ya + BM_ROWS, H - w2);
+    if (x >= W || ya >= yb) return;
+    const uint8_t* p = preL + (size_t)blockIdx.z * H * pitch + x;
     int s = 0;
-    for (int dy = -w2; dy <= w2; ++dy) s += abs((int)p[(size_t)(y + dy) * pitch + x] - cap);
-    tc[((size_t)blockIdx.z * H + y) * W + x] = (uint16_t)s;
+    for (int dy = -w2; dy <= w2; ++dy) s += abs((int)p[(size_t)(ya + dy) * pitch] - cap);
+    uint16_t* o = tc + (size_t)blockIdx.z * H * W + x;
+    for (int y = ya; y < yb; ++y) {
+        o[(size_t)y * W] = (uint16_t)s;
+        if (y + 1 < yb) s += abs((int)p[(size_t)(y + 1 + w2) * pitch] - cap) - abs((int)p[(size_t)(y - w2) * pitch] - cap);
+    }
 }
-__global__ void k_bm_tex_row(const uint16_t* __restrict__ tc, int W, int H, int w2, int* __restrict__ tex)
+// row pass: a warp slides along a row segment; lanes own BM_SEG consecutive columns each
+constexpr int BM_SEG = 8;
+__global__ void __launch_bounds__(128)
+k_bm_tex_row(const uint16_t* __restrict__ tc, int W, int H, int w2, int* __restrict__ tex)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x + w2, y = blockIdx.y + w2;
-    if (x >= W - w2 || y >= H - w2) return;
+    const int xa = (blockIdx.x * blockDim.x + threadIdx.x) * BM_SEG + w2, y = blockIdx.y + w2;
+    if (xa >= W - w2 || y >= H - w2) return;
     const size_t base = ((size_t)blockIdx.z * H + y) * W;
+    const int xb = min(xa + BM_SEG, W - w2);
     int s = 0;
-    for (int dx = -w2; dx <= w2; ++dx) s += tc[base + x + dx];
-    tex[base + x] = s;
+    for (int dx = -w2; dx <= w2; ++dx) s += tc[base + xa + dx];
+    for (int x = xa; x < xb; ++x) {
+        tex[base + x] = s;
+        if (x + 1 < xb) s += (int)tc[base + x + 1 + w2] - (int)tc[base + x - w2];
+    }
 }
 
 // column sums: lane (x', q) owns the eight disparity indices k = 8q..8q+7 of column x' and marches down the valid
 // rows with a sliding sum.  The eight right-image bytes start at an arbitrary byte address, so they are cut out of
 // three aligned words with PRMT (the selector is constant per thread); |L - R| is VABSDIFF4 on four bytes at once,
 // widened to packed u16x2 for the running sums; one 128-bit store per row.
-__device__ __forceinline__ void bm_ad8(const uint8_t* __restrict__ rowL, const unsigned* __restrict__ rowR, unsigned sel,
-                                       unsigned (&e)[4])
+__device__ __forceinline__ uint2 bm_ad8(const uint8_t* __restrict__ rowL, const unsigned* __restrict__ rowR, unsigned sel)
 {
     const unsigned lb = (unsigned)rowL[0] * 0x01010101u;
     const unsigned w0 = rowR[0], w1 = rowR[1], w2 = rowR[2];
-    const unsigned dlo = __vabsdiffu4(lb, __byte_perm(w0, w1, sel));
-    const unsigned dhi = __vabsdiffu4(lb, __byte_perm(w1, w2, sel));
-    e[0] = __byte_perm(dlo, 0, 0x4140); e[1] = __byte_perm(dlo, 0, 0x4342);
-    e[2] = __byte_perm(dhi, 0, 0x4140); e[3] = __byte_perm(dhi, 0, 0x4342);
+    return make_uint2(__vabsdiffu4(lb, __byte_perm(w0, w1, sel)), __vabsdiffu4(lb, __byte_perm(w1, w2, sel)));
+}
+// acc (packed u16x2) += the eight bytes of e, -= the eight bytes of f
+__device__ __forceinline__ void bm_acc(unsigned (&acc)[4], const uint2& e, const uint2& f)
+{
+    acc[0] += __byte_perm(e.x, 0, 0x4140) - __byte_perm(f.x, 0, 0x4140); acc[1] += __byte_perm(e.x, 0, 0x4342) - __byte_perm(f.x, 0, 0x4342);
+    acc[2] += __byte_perm(e.y, 0, 0x4140) - __byte_perm(f.y, 0, 0x4140); acc[3] += __byte_perm(e.y, 0, 0x4342) - __byte_perm(f.y, 0, 0x4342);
 }
 
+// The absolute differences of the last blockSize rows stay in a per-thread shared-memory ring (8 bytes per row), so
+// the row that leaves the window is not evaluated a second time.
 template <int G>
 __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ preL, const uint8_t* __restrict__ preR,
                                                    size_t pitch, int H, int width1, int D, int lofs, int w2,
                                                    uint16_t* __restrict__ col)
 {
-    constexpr int Dp = 8 * G;
+    extern __shared__ uint2 bm_ring[];          // [bs][128]
+    const int Dp = D;           // pixel stride of the column-sum volume: numDisp (a multiple of 16); idle lanes store nothing
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int xp = gtid / G, q = gtid % G;
     if (xp >= width1 || q * 8 >= D) return;
@@ -85,19 +110,24 @@ __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ p
     const unsigned sel = 0x3210u + 0x1111u * (unsigned)(ra & 3);
     const size_t pw = pitch / 4;                             // pitch is a multiple of 16 bytes
     const int bs = 2 * w2 + 1;
-    unsigned acc[4] = {0, 0, 0, 0}, e[4];
+    uint2* ring = bm_ring + threadIdx.x;
+    unsigned acc[4] = {0, 0, 0, 0};
     for (int y = 0; y < bs; ++y) {
-        bm_ad8(pl + (size_t)y * pitch, pr + (size_t)y * pw, sel, e);
-        acc[0] += e[0]; acc[1] += e[1]; acc[2] += e[2]; acc[3] += e[3];
+        const uint2 e = bm_ad8(pl + (size_t)y * pitch, pr + (size_t)y * pw, sel);
+        ring[y * 128] = e;
+        bm_acc(acc, e, make_uint2(0u, 0u));
     }
     uint16_t* out = col + ((size_t)blockIdx.y * H * width1 + xp) * Dp + q * 8;
+    int slot = 0;                                            // ring slot of the oldest row (y - w2)
+#pragma unroll 2
     for (int y = w2; y < H - w2; ++y) {
         st128(out + (size_t)y * width1 * Dp, make_uint4(acc[0], acc[1], acc[2], acc[3]));
         if (y + 1 < H - w2) {
-            unsigned f[4];
-            bm_ad8(pl + (size_t)(y + 1 + w2) * pitch, pr + (size_t)(y + 1 + w2) * pw, sel, e);
-            bm_ad8(pl + (size_t)(y - w2) * pitch, pr + (size_t)(y - w2) * pw, sel, f);
-            acc[0] += e[0] - f[0]; acc[1] += e[1] - f[1]; acc[2] += e[2] - f[2]; acc[3] += e[3] - f[3];
+            const uint2 e = bm_ad8(pl + (size_t)(y + 1 + w2) * pitch, pr + (size_t)(y + 1 + w2) * pw, sel);
+            const uint2 f = ring[slot * 128];
+            ring[slot * 128] = e;
+            bm_acc(acc, e, f);
+            if (++slot == bs) slot = 0;
         }
     }
 }
@@ -125,8 +155,10 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
     const bool active = r < nrows;
     if (!active) r = nrows - 1;
     const int f = (int)(r / vrows), y = (int)(r % vrows) + a.w2;
-    const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + q * 8;
+    const bool mem = q * 8 < a.D;               // lanes beyond numDisp hold no disparity: no loads, keys stay "infinite"
+    const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + (mem ? q * 8 : 0);
     const uint16_t* cp = a.col + rowBase;
+    const size_t outRow = ((size_t)f * a.H + y) * a.W;
     const int bs = 2 * a.w2 + 1;
     const unsigned kb = (unsigned)q * 8u;
 
@@ -135,19 +167,34 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
         const uint4 v = ld128(cp + (size_t)j * a.Dp);
         hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
     }
-    for (int xp = a.w2; xp < a.width1 - a.w2; ++xp) {
-        unsigned Sf[4] = {hs.x, hs.y, hs.z, hs.w};
-        unsigned keys[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned s = (j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu);
-            keys[j] = ((int)(kb + j) < a.D) ? ((s << 16) | (kb + j)) : 0xffffffffu;
+    // The per-pixel epilogue (texture test, sub-pixel division, store) is identical on the G lanes of a pixel, so it is
+    // deferred: lane q keeps the winner of every G-th step and the G lanes finish G pixels at once.
+    unsigned svKey = 0, svP = 0, svN = 0;
+    int svX = -1, sc = 0;
+    auto flush = [&]() {
+        if (svX >= 0 && active) {
+            const size_t oi = outRow + svX;
+            if (a.tex[oi] >= a.texThr) {
+                const int minsad = (int)(svKey >> 16), mind = (int)(svKey & 0xffffu);
+                const int p = (int)svP, n = (int)svN;
+                const int den = p + n - 2 * minsad + abs(p - n);
+                a.disp[oi] = (int16_t)((((a.D - 1 - mind) * 256) + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
+            }
         }
-        unsigned key = min(min(min(keys[0], keys[1]), min(keys[2], keys[3])), min(min(keys[4], keys[5]), min(keys[6], keys[7])));
+        svX = -1;
+    };
+    const int xEnd = a.width1 - a.w2;
+    for (int xp = a.w2; xp < xEnd; ++xp) {
+        const unsigned Sf[4] = {hs.x, hs.y, hs.z, hs.w};
+        // first argmin through (SAD << 16) | k keys: low halves by a shift-add, high halves by a mask-or, 32-bit min3
+        unsigned key = __vimin3_u32((Sf[0] << 16) + kb, (Sf[0] & 0xffff0000u) | (kb + 1), (Sf[1] << 16) + (kb + 2));
+        key = __vimin3_u32(key, (Sf[1] & 0xffff0000u) | (kb + 3), (Sf[2] << 16) + (kb + 4));
+        key = __vimin3_u32(key, (Sf[2] & 0xffff0000u) | (kb + 5), (Sf[3] << 16) + (kb + 6));
+        key = min(key, (Sf[3] & 0xffff0000u) | (kb + 7));
+        if (!mem) key = 0xffffffffu;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
         const int minsad = (int)(key >> 16), mind = (int)(key & 0xffffu);
-        const int X = xp + a.lofs;
         bool reject = false;
         if (a.uniq > 0) {
             const int thresh = minsad + (minsad * a.uniq / 100);
@@ -158,9 +205,9 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
                 const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
                 bad |= (k < a.D) && (k < mind - 1 || k > mind + 1) && (s <= thresh);
             }
-            const unsigned b = __ballot_sync(FULL, bad);
+            const unsigned bal = __ballot_sync(FULL, bad);
             const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
-            reject = (b & gmask) != 0u;
+            reject = (bal & gmask) != 0u;
         }
         const int ip = (mind + 1 < a.D) ? mind + 1 : a.D - 2;
         const int in = (mind > 0) ? mind - 1 : 1;
@@ -169,20 +216,15 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
             vp = __shfl_sync(FULL, vp, ip >> 3, G);
             vn = __shfl_sync(FULL, vn, in >> 3, G);
         }
-        if (active && q == 0) {
-            const size_t oi = ((size_t)f * a.H + y) * a.W + X;
-            if (!reject && a.tex[oi] >= a.texThr) {
-                const int p = (int)vp, n = (int)vn;
-                const int den = p + n - 2 * minsad + abs(p - n);
-                a.disp[oi] = (int16_t)((((a.D - 1 - mind) * 256) + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
-            }
-        }
-        if (xp + 1 < a.width1 - a.w2) {
+        if (sc == q) { svKey = key; svP = vp; svN = vn; svX = reject ? -1 : xp + a.lofs; }
+        if (++sc == G) { flush(); sc = 0; }
+        if (xp + 1 < xEnd) {
             const uint4 nx = ld128(cp + (size_t)(xp + 1 + a.w2) * a.Dp);
             const uint4 od = ld128(cp + (size_t)(xp - a.w2) * a.Dp);
             hs.x += nx.x - od.x; hs.y += nx.y - od.y; hs.z += nx.z - od.z; hs.w += nx.w - od.w;
         }
     }
+    flush();
 }
 
 __global__ void k_fill16(int16_t* p, size_t n, int16_t v)
@@ -207,28 +249,39 @@ void launch_bm(mvsv_ctx* c, int B)
     const size_t npx = (size_t)B * W * H;
     { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
     {
-        dim3 blk(128), grd((W + 127) / 128, H, 2 * B);
+        dim3 blk(128), grd((W + 127) / 128, (H + BM_ROWS - 1) / BM_ROWS, 2 * B);
         KernelTimer kt(c, KID_BM_PREFILTER);
         k_bm_prefilter<<<grd, blk, 0, c->stream>>>(c->rect[0], c->rect[1], c->pitch, W, H, n.cap, c->bm_pre[0], c->bm_pre[1]);
     }
     const bool any = !(n.lofs >= W || n.width1 < 1) && (H - 2 * n.w2 > 0) && (n.width1 - 2 * n.w2 > 0);
     if (!any) return;
     {
-        dim3 blk(128), grd((W + 127) / 128, H - 2 * n.w2, B);
+        dim3 blk(128), grd((W + 127) / 128, (H - 2 * n.w2 + BM_ROWS - 1) / BM_ROWS, B);
         { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_col<<<grd, blk, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex); }
-        dim3 grd2((W - 2 * n.w2 + 127) / 128, H - 2 * n.w2, B);
+        dim3 grd2((W - 2 * n.w2 + 128 * BM_SEG - 1) / (128 * BM_SEG), H - 2 * n.w2, B);
         { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2); }
     }
     {
         const long long threads = (long long)n.width1 * n.G;
         dim3 grd((unsigned)((threads + 127) / 128), B);
+        // blockSize^2 * 2 * cap <= 65535 (contract) bounds blockSize by 181: the ring needs at most 181 KB
+        const size_t ringBytes = (size_t)n.bs * 128 * sizeof(uint2);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_bm_colsum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            configured = true;
+        }
         KernelTimer kt(c, KID_BM_COLSUM);
         switch (n.G) {
-            case 2: k_bm_colsum<2><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 4: k_bm_colsum<4><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 8: k_bm_colsum<8><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 16: k_bm_colsum<16><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            default: k_bm_colsum<32><<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 2: k_bm_colsum<2><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 4: k_bm_colsum<4><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 8: k_bm_colsum<8><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            case 16: k_bm_colsum<16><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
+            default: k_bm_colsum<32><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
         }
     }
     BmArgs a;

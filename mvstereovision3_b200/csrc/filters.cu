@@ -42,29 +42,51 @@ __global__ void k_rectify_maps(RectifyCoef q, int rx, int ry, int rw, int rh, in
 
 __device__ __forceinline__ int sat16(int v) { return max(-32768, min(32767, v)); }
 
-__global__ void k_remap(const uint8_t* __restrict__ src, size_t spitch, int fw, int fh, const int2* __restrict__ map,
-                        uint8_t* __restrict__ dst, size_t dpitch, int W, int H)
+// One thread = four neighbouring output pixels of up to RM_FRAMES frames: the map entries and the bilinear weights are
+// the same for every frame of the batch, so they are fetched and expanded once and only the four taps per pixel are
+// gathered per frame; the four results leave as one 32-bit store.
+constexpr int RM_FRAMES = 8;
+
+__global__ void __launch_bounds__(128)
+k_remap(const uint8_t* __restrict__ src, size_t spitch, int fw, int fh, const int2* __restrict__ map,
+        uint8_t* __restrict__ dst, size_t dpitch, int W, int H, int B)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
-    const int2 m = map[(size_t)y * W + x];
-    const int sx = sat16(m.x >> 5), sy = sat16(m.y >> 5), fx = m.x & 31, fy = m.y & 31;
-    const uint8_t* s = src + (size_t)f * fh * spitch;
-    int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
-    const bool x0 = sx >= 0 && sx < fw, x1 = sx + 1 >= 0 && sx + 1 < fw;
-    if (sy >= 0 && sy < fh) {
-        const uint8_t* r = s + (size_t)sy * spitch;
-        if (x0) p00 = r[sx];
-        if (x1) p01 = r[sx + 1];
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= W) return;
+    const int f0 = blockIdx.z * RM_FRAMES, f1 = min(f0 + RM_FRAMES, B);
+    int off[4][4];              // byte offsets of the four taps inside a frame, -1 = outside (BORDER_CONSTANT 0)
+    int wgt[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = min(x4 + k, W - 1);
+        const int2 m = map[(size_t)y * W + x];
+        const int sx = sat16(m.x >> 5), sy = sat16(m.y >> 5), fx = m.x & 31, fy = m.y & 31;
+        const bool x0 = sx >= 0 && sx < fw, x1 = sx + 1 >= 0 && sx + 1 < fw;
+        const bool y0 = sy >= 0 && sy < fh, y1 = sy + 1 >= 0 && sy + 1 < fh;
+        off[k][0] = (y0 && x0) ? sy * (int)spitch + sx : -1;
+        off[k][1] = (y0 && x1) ? sy * (int)spitch + sx + 1 : -1;
+        off[k][2] = (y1 && x0) ? (sy + 1) * (int)spitch + sx : -1;
+        off[k][3] = (y1 && x1) ? (sy + 1) * (int)spitch + sx + 1 : -1;
+        wgt[k][0] = (32 - fx) * (32 - fy) * 32; wgt[k][1] = fx * (32 - fy) * 32;
+        wgt[k][2] = (32 - fx) * fy * 32; wgt[k][3] = fx * fy * 32;
     }
-    if (sy + 1 >= 0 && sy + 1 < fh) {
-        const uint8_t* r = s + (size_t)(sy + 1) * spitch;
-        if (x0) p10 = r[sx];
-        if (x1) p11 = r[sx + 1];
+    for (int f = f0; f < f1; ++f) {
+        const uint8_t* s = src + (size_t)f * fh * spitch;
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int acc = 16384;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc += (off[k][t] >= 0 ? (int)s[off[k][t]] : 0) * wgt[k][t];
+            out |= (unsigned)max(0, min(255, acc >> 15)) << (8 * k);
+        }
+        uint8_t* d = dst + ((size_t)f * H + y) * dpitch + x4;
+        if (x4 + 3 < W) {
+            *reinterpret_cast<unsigned*>(d) = out;          // dpitch and x4 are multiples of 4
+        } else {
+            for (int k = 0; x4 + k < W; ++k) d[k] = (uint8_t)(out >> (8 * k));
+        }
     }
-    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
-    const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 16384) >> 15;
-    dst[((size_t)f * H + y) * dpitch + x] = (uint8_t)max(0, min(255, v));
 }
 
 // cv::resize(src, dst, Size(0,0), f, f) for CV_8UC1, default INTER_LINEAR (reference src/Stereosystem.cpp:294-295):
@@ -323,53 +345,72 @@ k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const in
 // ------------------------------------------------------------------------------------------------
 struct QMat { float q[16]; };
 
-__global__ void k_xyz(const int16_t* __restrict__ disp, float* __restrict__ xyz, int W, int H, QMat Q)
+// One thread = four consecutive pixels of the batch's linear pixel index: one 8-byte load, three 16-byte stores.
+__global__ void __launch_bounds__(256) k_xyz(const int16_t* __restrict__ disp, float* __restrict__ xyz, int W, int H, size_t npx, QMat Q)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
-    const size_t i = ((size_t)blockIdx.z * H + y) * W + x;
-    const float value = (float)disp[i];
-    float X = 0.f, Y = 0.f, Z = 0.f;
-    if (value > 0.f) {
-        const float in[4] = {(float)x, (float)y, value / 16.f, 1.f};
-        float c[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            double acc = 0.0;   // cv::Mat_<float> product accumulates in double
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc += (double)Q.q[r * 4 + k] * (double)in[k];
-            c[r] = (float)acc;
-        }
-        X = c[0] / c[3]; Y = c[1] / c[3]; Z = c[2] / c[3];
-        if (isinf(Z / 1000.f)) Z = 0.f;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= npx) return;
+    short v4[4] = {0, 0, 0, 0};
+    if (i0 + 3 < npx) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(disp + i0);
+        v4[0] = (short)(raw.x & 0xffffu); v4[1] = (short)(raw.x >> 16); v4[2] = (short)(raw.y & 0xffffu); v4[3] = (short)(raw.y >> 16);
+    } else {
+        for (int k = 0; i0 + k < npx; ++k) v4[k] = disp[i0 + k];
     }
-    xyz[i * 3 + 0] = X; xyz[i * 3 + 1] = Y; xyz[i * 3 + 2] = Z;
+    const size_t row = i0 / W;
+    int x = (int)(i0 - row * W), y = (int)(row % H);
+    float o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float value = (float)v4[k];
+        float X = 0.f, Y = 0.f, Z = 0.f;
+        if (value > 0.f) {
+            const float in[4] = {(float)x, (float)y, value / 16.f, 1.f};
+            float cc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                double acc = 0.0;   // cv::Mat_<float> product accumulates in double
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc += (double)Q.q[r * 4 + j] * (double)in[j];
+                cc[r] = (float)acc;
+            }
+            X = cc[0] / cc[3]; Y = cc[1] / cc[3]; Z = cc[2] / cc[3];
+            if (isinf(Z / 1000.f)) Z = 0.f;
+        }
+        o[3 * k] = X; o[3 * k + 1] = Y; o[3 * k + 2] = Z;
+        if (++x == W) { x = 0; if (++y == H) y = 0; }
+    }
+    float* dst = xyz + i0 * 3;
+    if (i0 + 3 < npx) {
+        float4* d4 = reinterpret_cast<float4*>(dst);           // i0 is a multiple of 4: 48-byte aligned groups
+        d4[0] = make_float4(o[0], o[1], o[2], o[3]); d4[1] = make_float4(o[4], o[5], o[6], o[7]); d4[2] = make_float4(o[8], o[9], o[10], o[11]);
+    } else {
+        for (int k = 0; i0 + k < npx; ++k) { dst[3 * k] = o[3 * k]; dst[3 * k + 1] = o[3 * k + 1]; dst[3 * k + 2] = o[3 * k + 2]; }
+    }
 }
 
-__global__ void k_means(const int16_t* __restrict__ disp, const int* __restrict__ rois, float* __restrict__ means,
-                        int W, int H, int nrois)
+// One warp per ROI (and frame): lanes walk the ROI row by row, no division per element; a CTA holds MEANS_WARPS ROIs.
+constexpr int MEANS_WARPS = 8;
+
+__global__ void __launch_bounds__(MEANS_WARPS * 32)
+k_means(const int16_t* __restrict__ disp, const int* __restrict__ rois, float* __restrict__ means, int W, int H, int nrois)
 {
-    const int r = blockIdx.x, f = blockIdx.y;
-    const int x0 = rois[r * 4 + 0], y0 = rois[r * 4 + 1], w = rois[r * 4 + 2], h = rois[r * 4 + 3];
-    const int16_t* img = disp + (size_t)f * W * H;
+    const int r = blockIdx.x * MEANS_WARPS + (threadIdx.x >> 5), f = blockIdx.y, lane = threadIdx.x & 31;
+    if (r >= nrois) return;
+    const int4 roi = *reinterpret_cast<const int4*>(rois + r * 4);      // x, y, w, h
+    const int16_t* img = disp + (size_t)f * W * H + (size_t)roi.y * W + roi.x;
     int total = 0, n = 0;
-    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-        const int v = img[(size_t)(y0 + i / w) * W + x0 + i % w];
-        if (v > 1) { total += v; ++n; }
-    }
-    __shared__ int st[32], sn[32];
+    for (int yy = 0; yy < roi.w; ++yy, img += W)
+        for (int xx = lane; xx < roi.z; xx += 32) {
+            const int v = img[xx];
+            if (v > 1) { total += v; ++n; }
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         total += __shfl_xor_sync(0xffffffffu, total, o);
         n += __shfl_xor_sync(0xffffffffu, n, o);
     }
-    if ((threadIdx.x & 31) == 0) { st[threadIdx.x >> 5] = total; sn[threadIdx.x >> 5] = n; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        total = 0; n = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { total += st[i]; n += sn[i]; }
-        means[(size_t)f * nrois + r] = (total == 0 || n == 0) ? 0.f : (float)(total / n);
-    }
+    if (lane == 0) means[(size_t)f * nrois + r] = (total == 0 || n == 0) ? 0.f : (float)(total / n);
 }
 
 __global__ void k_minmax_init(int* mm, int n)
@@ -425,10 +466,10 @@ void launch_remap(mvsv_ctx* c, int cam, int B)
 {
     const int rw = c->roi[2], rh = c->roi[3];
     const bool resized = c->resize_factor > 0.0;
-    dim3 blk(128), grd((rw + 127) / 128, rh, B);
+    dim3 blk(128), grd((rw + 511) / 512, rh, (B + RM_FRAMES - 1) / RM_FRAMES);
     KernelTimer kt(c, KID_REMAP);
     k_remap<<<grd, blk, 0, c->stream>>>(c->raw[cam], c->raw_pitch, c->fw, c->fh, c->map_xy[cam],
-                                        resized ? c->crop[cam] : c->rect[cam], resized ? c->crop_pitch : c->pitch, rw, rh);
+                                        resized ? c->crop[cam] : c->rect[cam], resized ? c->crop_pitch : c->pitch, rw, rh, B);
 }
 
 void launch_resize(mvsv_ctx* c, int cam, int B)
@@ -471,15 +512,15 @@ void launch_xyz(mvsv_ctx* c, int B)
 {
     QMat Q;
     for (int i = 0; i < 16; ++i) Q.q[i] = c->Q[i];
-    dim3 blk(128), grd((c->W + 127) / 128, c->H, B);
+    const size_t npx = (size_t)B * c->H * c->W;
     KernelTimer kt(c, KID_XYZ);
-    k_xyz<<<grd, blk, 0, c->stream>>>(c->disp, c->xyz, c->W, c->H, Q);
+    k_xyz<<<(unsigned)((npx / 4 + 256) / 256), 256, 0, c->stream>>>(c->disp, c->xyz, c->W, c->H, npx, Q);
 }
 
 void launch_means(mvsv_ctx* c, int B)
 {
     if (c->nrois <= 0) return;
-    dim3 grd(c->nrois, B);
+    dim3 grd((c->nrois + MEANS_WARPS - 1) / MEANS_WARPS, B);
     KernelTimer kt(c, KID_MEANS);
-    k_means<<<grd, 128, 0, c->stream>>>(c->disp, c->rois, c->means, c->W, c->H, c->nrois);
+    k_means<<<grd, MEANS_WARPS * 32, 0, c->stream>>>(c->disp, c->rois, c->means, c->W, c->H, c->nrois);
 }
