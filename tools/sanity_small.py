@@ -14,7 +14,7 @@ from mvstereovision3_b200 import api, synth  # noqa: E402
 H, W = 40, 150
 l, r = synth.random_pair(H, W, seed=1)
 L, R = np.stack([l, r]), np.stack([r, l])
-for mode, nd, flags in ((0, 64, 0), (1, 24, 0), (1, 16, 0x200), (0, 32, 0xff00), (0, 8, 0)):
+for mode, nd, flags in ((0, 64, 0), (1, 24, 0), (1, 16, 0x200), (0, 32, 0xff00), (0, 8, 0), (1, 128, 0x400), (0, 256, 0x900)):
     with api.Engine(W, H, max_batch=2) as e:
         e.set_sgbm_params(minDisp=1, numDisp=nd, blockSize=5, P1=8, P2=32, disp12MaxDiff=1, preFilterCap=31,
                           uniquenessRatio=10, speckleWindowSize=20, speckleRange=2, disparityMode=mode)
