@@ -19,9 +19,10 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-// compute threads of the cost kernel: 256, or 512 when a pixel needs >= 16 lanes (D > 64), so that the staging of
-// the right-image entries (PX - 1 + Dp per row) is amortised over more columns
-constexpr int vs_compute_threads(int G) { return G >= 16 ? 512 : 256; }
+// compute threads of the cost kernel: 512 when a pixel needs >= 8 lanes (D > 32), so that the staging of the right-image
+// entries (PX - 1 + Dp per row, eight shifted copies each) is amortised over more columns, else 256.  Measured at cfg 2
+// (D = 64): 256 threads 3.16 ms, 512 threads 2.82 ms, 768 threads 3.59 ms; at D = 128 768 threads lose (2.62 -> 3.26 ms)
+constexpr int vs_compute_threads(int G) { return G >= 8 ? 512 : 256; }
 
 // ------------------------------------------------------------------------------------------------
 // K2a: prefilter (A.2: sob/raw channels with ftzero borders, lo/hi half-sample bounds).

@@ -486,22 +486,19 @@ cudaError_t launch_fast(const SweepArgs& a0, int nthr, size_t smem, cudaStream_t
     cfg.gridDim = dim3(a.NS * a.NF, 1, 1); cfg.blockDim = dim3(nthr, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     if (a.dsm) {
-        // the strips of a frame are one thread-block cluster (co-scheduled by the hardware); frames are independent
+        // the strips of a frame as one thread-block cluster (co-scheduled by the hardware; frames are independent) --
+        // but only if as many clusters fit at once as frames are planned to be in flight: a GPC holds a whole number of
+        // clusters, and e.g. clusters of 4 strand 16 of the 148 SMs, which would cost a whole extra wave of frames
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = a.NS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    } else {
-        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;  // all CTAs co-resident: they wait on one another
-    }
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (a.dsm) {
-        // frames in flight = clusters that can be resident at once (a GPC holds a whole number of clusters)
+        cfg.attrs = at; cfg.numAttrs = 1;
         int nmax = 0;
-        if (cudaOccupancyMaxActiveClusters(&nmax, k_sweep<NR, G, PAD, MODE>, &cfg) != cudaSuccess || nmax < 1) {
-            cudaGetLastError();
-            nmax = a.NF;
-        }
-        a.NF = std::min(a.NF, nmax);
-        cfg.gridDim = dim3(a.NS * a.NF, 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&nmax, k_sweep<NR, G, PAD, MODE>, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+        if (nmax < a.NF) a.dsm = 0;
+    }
+    if (!a.dsm) {
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;  // all CTAs co-resident: they wait on one another
+        cfg.attrs = at; cfg.numAttrs = 1;
     }
     return cudaLaunchKernelEx(&cfg, k_sweep<NR, G, PAD, MODE>, a);
 }
