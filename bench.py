@@ -62,6 +62,8 @@ HEADLINE = "cfg2"
 # (int16 volumes; images, maps and per-pixel outputs are < 1 % and ignored) -- see DESIGN.md "Kernels"
 KERNEL_BYTES_PER_CELL = {"sgbm_vsum": 2.0, "sgbm_h1": 6.0, "sgbm_td": 6.0, "sgbm_vdir": 6.0, "sgbm_h2_wta": 4.0,
                          "bm_colsum": 2.0, "bm_wta": 2.0}
+# the same when the aggregated volume S is kept as one byte per cell (mvsv_info.sgbm_s8: npaths * P2 <= 255)
+KERNEL_BYTES_PER_CELL_S8 = dict(KERNEL_BYTES_PER_CELL, sgbm_h1=5.0, sgbm_td=4.0, sgbm_h2_wta=3.0)
 NCU_SUMMARY = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
 
 
@@ -462,9 +464,10 @@ def run_config(cx, key, batch, steps, warmup, detail=False):
                              "frac": spec["model_bpc"] * cells * fps / cx.world / 1e9 / peak},
            "kernel_ms_per_step": {k: v[0] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
            "sweep_strips_per_frame": eng.info.sgbm_td_cluster if spec["kind"] != "bm" else None,
+           "s_volume": None if spec["kind"] == "bm" else ("u8 excess over npaths*C" if eng.info.sgbm_s8 else "u16"),
            "parity": parity}
     if detail:
-        out["_detail"] = dict(prof=prof, launches=launches, clocks=clocks, gen=gen, uniq=uniq, gpu_disp=gpu_disp,
+        out["_detail"] = dict(s8=bool(eng.info.sgbm_s8), prof=prof, launches=launches, clocks=clocks, gen=gen, uniq=uniq, gpu_disp=gpu_disp,
                               cells=cells, fps=fps, fps_e2e=fps_e2e, ms_max=ms_max, ms_e2e_max=ms_e2e_max, d2h=d2h)
     eng.close()
     for b in (hl, hr, hd[0], hd[1]):
@@ -540,19 +543,20 @@ def main():
     cells = det["cells"]
     cells_per_launch = cells * B
     prof = det["prof"]
+    kbytes = KERNEL_BYTES_PER_CELL_S8 if det["s8"] else KERNEL_BYTES_PER_CELL
     kern = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / v[1]} for k, v in prof.items()}
     total_kernel_ms = sum(v["ms_total"] for v in kern.values())
     for k, v in kern.items():
         v["share"] = v["ms_total"] / total_kernel_ms if total_kernel_ms else 0.0
-        if k in KERNEL_BYTES_PER_CELL:
-            v["algorithmic_GBps"] = KERNEL_BYTES_PER_CELL[k] * cells_per_launch / (v["ms_per_launch"] * 1e-3) / 1e9
+        if k in kbytes:
+            v["algorithmic_GBps"] = kbytes[k] * cells_per_launch / (v["ms_per_launch"] * 1e-3) / 1e9
     dom = max(kern, key=lambda k: kern[k]["ms_total"])
     tpc = (ncu.get("dram_bytes_per_cell") or {}).get(dom)
-    if dom in KERNEL_BYTES_PER_CELL:
+    if dom in kbytes:
         ach = kern[dom]["algorithmic_GBps"]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": (tpc * cells_per_launch if tpc is not None else None), "peak_source": peak_src,
-                    "bytes_per_cell": KERNEL_BYTES_PER_CELL[dom], "cells_per_launch": cells_per_launch,
+                    "bytes_per_cell": kbytes[dom], "cells_per_launch": cells_per_launch,
                     "ms_per_launch": kern[dom]["ms_per_launch"], "share_of_step": kern[dom]["share"]}
     else:
         roofline = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
@@ -567,7 +571,7 @@ def main():
     roofline_int["frac"] = roofline_int["achieved"] / ipeak if roofline_int["achieved"] else None
     # whole-path figure against the 8 B/cell aggregation model of SURVEY.md 8(d)
     roofline_path = dict(head["roofline_path"], note="per GPU; whole step (all kernels) against the 8 B/cell model",
-                         step_bytes_per_cell=sum(KERNEL_BYTES_PER_CELL.get(k, 0.0) * v["launches"] / args.steps for k, v in kern.items()))
+                         step_bytes_per_cell=sum(kbytes.get(k, 0.0) * v["launches"] / args.steps for k, v in kern.items()))
 
     # ---- CPU baseline on this box's host cores (bounded sample) + parity gate on the frames it computed ---------
     cpu = None

@@ -202,7 +202,7 @@ __host__ __device__ constexpr int sweep_lbw(int NR) { return ((NR / 4) | 1) * 4;
 // and the S volume holds one BYTE per cell: (sum of the paths so far) - (paths so far) * C, which is the sum of the
 // paths' excesses L - C, each in [0, P2]; the host checks npaths * P2 <= 255.  The sweep then adds the byte
 // (L1 + L2 + L3 - 3 C) and moves half as many S bytes.
-template <int NR, int G, bool PAD, int MODE>
+template <int NR, int G, bool PAD, int MODE, bool DSM>
 __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
 {
     constexpr bool FAST = MODE >= 1, S8 = MODE == 2;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
     // border records received through distributed shared memory: rec[dir][NSLOT][HBW] words, 16-byte aligned
     const int HBW = a.Dp / 2 + 4;
     unsigned* const rec = smem + (((size_t)(prog2 + nw - reinterpret_cast<int*>(smem)) + 3) & ~(size_t)3);
-    const bool dsm = a.dsm != 0;
+    constexpr bool dsm = DSM;   // compile time: the extra branches cost the D = 256 instances 5 % when they were run-time
 
     if (tid < nw) { prog1[tid] = 0; prog2[tid] = 0; }
     if (dsm) {
@@ -472,35 +472,51 @@ size_t sweep_smem_bytes(int NR, int G, int Mmax, int nthr)
     return words * 4;
 }
 
-template <int NR, int G, bool PAD, int MODE>
-cudaError_t launch_fast(const SweepArgs& a0, int nthr, size_t smem, cudaStream_t st)
+// One launch.  DSM: the strips of a frame as one thread-block cluster (co-scheduled by the hardware; frames are
+// independent), border records through distributed shared memory -- used only if as many clusters fit at once as frames
+// are planned to be in flight: a GPC holds a whole number of clusters, and e.g. clusters of 4 strand 16 of the 148 SMs,
+// which would cost a whole extra wave of frames (*fits reports it).  Otherwise: cooperative launch (all CTAs
+// co-resident: they wait on one another), records through global memory.
+template <int NR, int G, bool PAD, int MODE, bool DSM>
+cudaError_t launch_one(const SweepArgs& a, int nthr, size_t smem, cudaStream_t st, bool* fits)
 {
-    SweepArgs a = a0;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep<NR, G, PAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<NR, G, PAD, MODE, DSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.NS * a.NF, 1, 1); cfg.blockDim = dim3(nthr, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
-    if (a.dsm) {
-        // the strips of a frame as one thread-block cluster (co-scheduled by the hardware; frames are independent) --
-        // but only if as many clusters fit at once as frames are planned to be in flight: a GPC holds a whole number of
-        // clusters, and e.g. clusters of 4 strand 16 of the 148 SMs, which would cost a whole extra wave of frames
+    if (DSM) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = a.NS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int nmax = 0;
-        if (cudaOccupancyMaxActiveClusters(&nmax, k_sweep<NR, G, PAD, MODE>, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
-        if (nmax < a.NF) a.dsm = 0;
-    }
-    if (!a.dsm) {
-        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;  // all CTAs co-resident: they wait on one another
+        if (cudaOccupancyMaxActiveClusters(&nmax, k_sweep<NR, G, PAD, MODE, DSM>, &cfg) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+        *fits = nmax >= a.NF;
+        if (!*fits) return cudaSuccess;
+    } else {
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
     }
-    return cudaLaunchKernelEx(&cfg, k_sweep<NR, G, PAD, MODE>, a);
+    return cudaLaunchKernelEx(&cfg, k_sweep<NR, G, PAD, MODE, DSM>, a);
+}
+
+template <int NR, int G, bool PAD, int MODE>
+cudaError_t launch_fast(const SweepArgs& a, int nthr, size_t smem, cudaStream_t st)
+{
+    // the cluster variant only exists for one lane per pixel (D <= 64: cfg 2 and the reference's other 752x480 uses)
+    if constexpr (G == 1) {
+        if (a.dsm) {
+            bool fits = false;
+            const cudaError_t e = launch_one<NR, G, PAD, MODE, true>(a, nthr, smem, st, &fits);
+            if (e != cudaSuccess || fits) return e;
+        }
+    }
+    bool unused = true;
+    return launch_one<NR, G, PAD, MODE, false>(a, nthr, smem, st, &unused);
 }
 
 template <int NR, int G, bool PAD>
