@@ -54,7 +54,7 @@ CONFIGS = {
                                model_bpc=14.0),
     "cfg5_4k_d256": dict(name="cfg5: StereoSGBM MODE_SGBM 3840x2160 numDisp=256 blockSize=5 P1=200 P2=800", kind="sgbm",
                          H=2160, W=3840, params=dict(CFG4_PARAMS, disparityMode=0, uniquenessRatio=0, disp12MaxDiff=0,
-                                                     speckleWindowSize=0, speckleRange=0), batch=8, model_bpc=8.0),
+                                                     speckleWindowSize=0, speckleRange=0), batch=9, model_bpc=8.0),
 }
 HEADLINE = "cfg2"
 
