@@ -380,7 +380,7 @@ struct AggArgs {
     int storeS;
     // S8: the S volume holds, per cell, the byte (sum of the paths so far) - (paths so far) * C (see sweep.cu)
     uint16_t* Sdbg;             // where the final S goes when the test hook asks for it in S8 mode (the dead VS volume)
-    unsigned nprevPk, kclampPk; // S8: paths accumulated before the last scan, and ceil(32767 / that), both packed x2
+    unsigned nprevPk, kclampPk; // S8: number of paths, and ceil(32767 / that), both packed x2
 };
 
 // The row scans stream their operands through a per-lane shared-memory ring filled by cp.async (LDGSTS): the
@@ -579,22 +579,23 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     auto step = [&](const uint4& Cq, const uint4& Sq, int xi) {
         sgm_step<G, PAD>(L, mm, Cq, a.P1P1, a.P2P2, q, padLane);
         unsigned Sf[4];
-        uint4 Si = Sq;
         if (S8) {
-            // sum of the n paths before this one = n * C + byte.  With c' = min(C, ceil(32767 / n)) the product
-            // n * c' + byte fits 16 bits and is >= 32767 exactly when the true sum is: saturate afterwards.
+            // Sum of all paths = (n + 1) * C + byte + (L - C), n paths before this one.  With c' = min(C, ceil(32767 / (n+1)))
+            // the product (n + 1) * c' plus the small excess fits 16 bits and reaches 32767 exactly when the true sum does:
+            // one clamp, one multiply-add and one saturation per register instead of rebuilding S and adding L.
             const unsigned b0 = __byte_perm(Sq.x, 0, 0x4140), b1 = __byte_perm(Sq.x, 0, 0x4342);
             const unsigned b2 = __byte_perm(Sq.y, 0, 0x4140), b3 = __byte_perm(Sq.y, 0, 0x4342);
-            const unsigned n1 = a.nprevPk & 0xffffu;
-            Si.x = __vminu2(__vminu2(Cq.x, a.kclampPk) * n1 + b0, MVSV_PK_MAX);
-            Si.y = __vminu2(__vminu2(Cq.y, a.kclampPk) * n1 + b1, MVSV_PK_MAX);
-            Si.z = __vminu2(__vminu2(Cq.z, a.kclampPk) * n1 + b2, MVSV_PK_MAX);
-            Si.w = __vminu2(__vminu2(Cq.w, a.kclampPk) * n1 + b3, MVSV_PK_MAX);
+            const unsigned n1 = a.nprevPk & 0xffffu;          // n + 1
+            Sf[0] = __vminu2(__vminu2(Cq.x, a.kclampPk) * n1 + (b0 + L[0] - Cq.x), MVSV_PK_MAX);
+            Sf[1] = __vminu2(__vminu2(Cq.y, a.kclampPk) * n1 + (b1 + L[1] - Cq.y), MVSV_PK_MAX);
+            Sf[2] = __vminu2(__vminu2(Cq.z, a.kclampPk) * n1 + (b2 + L[2] - Cq.z), MVSV_PK_MAX);
+            Sf[3] = __vminu2(__vminu2(Cq.w, a.kclampPk) * n1 + (b3 + L[3] - Cq.w), MVSV_PK_MAX);
+        } else {
+            Sf[0] = __viaddmin_u16x2(Sq.x, L[0], MVSV_PK_MAX);
+            Sf[1] = __viaddmin_u16x2(Sq.y, L[1], MVSV_PK_MAX);
+            Sf[2] = __viaddmin_u16x2(Sq.z, L[2], MVSV_PK_MAX);
+            Sf[3] = __viaddmin_u16x2(Sq.w, L[3], MVSV_PK_MAX);
         }
-        Sf[0] = __viaddmin_u16x2(Si.x, L[0], MVSV_PK_MAX);
-        Sf[1] = __viaddmin_u16x2(Si.y, L[1], MVSV_PK_MAX);
-        Sf[2] = __viaddmin_u16x2(Si.z, L[2], MVSV_PK_MAX);
-        Sf[3] = __viaddmin_u16x2(Si.w, L[3], MVSV_PK_MAX);
         if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
         if (a.storeS && active && mem) st128(sdbg + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
         // ---- first argmin via (S << 16 | k) keys
@@ -744,8 +745,8 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     c->last_s8 = s8;
     a.Sdbg = c->VS;
     {
-        const unsigned nprev = (unsigned)(n.npaths - 1), kcl = (32767u + nprev - 1) / nprev;
-        a.nprevPk = nprev * 0x10001u; a.kclampPk = kcl * 0x10001u;
+        const unsigned nall = (unsigned)n.npaths, kcl = (32767u + nall - 1) / nall;     // all paths, see k_sgbm_h2_wta
+        a.nprevPk = nall * 0x10001u; a.kclampPk = kcl * 0x10001u;
     }
     launch_vsum(0, B);
     {

@@ -511,7 +511,8 @@ def test_sweep_walks_several_frames_per_cta(oracle, D, nc, B):
     dict(numDisp=256, blockSize=3, P1=2, P2=31, mode=1),                                          # four lanes, MODE_HH
     dict(numDisp=48, blockSize=7, P1=10, P2=50, preFilterCap=63),                                 # 24 registers per lane
     dict(numDisp=16, blockSize=11, P1=1, P2=2, preFilterCap=100),                                 # costs near the int16 limit
-], ids=["cfg2", "hh_d32", "d128", "d256_hh", "d48", "d16_wide"])
+    dict(numDisp=16, blockSize=11, P1=1, P2=2, preFilterCap=31, mode=1),                          # byte form with saturated sums
+], ids=["cfg2", "hh_d32", "d128", "d256_hh", "d48", "d16_wide", "d16_hh_saturating"])
 def test_byte_form_of_S_equals_16bit_form(oracle, kw):
     """When npaths * P2 <= 255 the aggregated volume is kept as one byte per cell (sum of the paths' excesses over
     C); the same parameters with the byte form forced off (debug flag bit 1) and the oracle must give the same final S
@@ -533,6 +534,8 @@ def test_byte_form_of_S_equals_16bit_form(oracle, kw):
     assert res[1][2] == (1 if fast else 0) and res[3][2] == 0, "byte form expected by default (row sums fit 16 bits), 16-bit form when forced"
     for b, (a_, b_) in enumerate(((l, r), (l2, r2))):
         disp, Cv, Sv, rawv = oracle.sgbm(a_, b_, p, want_volumes=True, want_raw=True)
+        if kw.get("mode") == 1 and kw["blockSize"] == 11 and b == 0:
+            assert (Sv == 32767).sum() > 10, "this case is meant to saturate some path sums"
         for flags in (1, 3):
             check("S/%d/%d" % (flags, b), res[flags][1][b], Sv)
             check("disp/%d/%d" % (flags, b), res[flags][0][b], disp)
