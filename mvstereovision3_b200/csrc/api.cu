@@ -128,6 +128,7 @@ int normalise_sgbm(mvsv_ctx* c, const mvsv_sgbm_params* p, SgbmNorm* n)
     n->npaths = n->mode ? 8 : 5;
     n->speckleWin = p->speckleWindowSize;
     n->speckleRange = p->speckleRange;
+    n->vsWide = 0;
     if (n->ftzero > 127) return fail(c, MVSV_ERR_INVALID, "preFilterCap > 127 is outside the supported range");
     if (n->uniq > 100) return fail(c, MVSV_ERR_INVALID, "uniquenessRatio > 100");
     const long long eff = 2 * n->SH2 + 1;
@@ -135,6 +136,7 @@ int normalise_sgbm(mvsv_ctx* c, const mvsv_sgbm_params* p, SgbmNorm* n)
         return fail(c, MVSV_ERR_INVALID,
                     "blockSize^2*(2*ftzero+63)+P2 > 32767: int16 overflow regime of OpenCV is outside the bit-exact contract");
     if (n->INV < -32768 || (n->maxD) * 16 > 32767) return fail(c, MVSV_ERR_INVALID, "disparity range does not fit CV_16S");
+    n->vsWide = sgbm_vsum_wide(*n) ? 1 : 0;
     if (n->W1 > 0 && (long long)c->H * n->W1 * n->Dp >= (1ll << 31))
         return fail(c, MVSV_ERR_UNSUPPORTED, "cost volume of one frame exceeds 2^31 cells");
     return MVSV_OK;

@@ -18,6 +18,7 @@ struct SgbmNorm {
     int bs, SW2, SH2, ftzero, uniq, d12, P1, P2;
     int maxD, minX1, maxX1, W1, INV, mode, npaths;
     int speckleWin, speckleRange;
+    int vsWide;                  // cost kernel with 768 compute threads (D > 128 and the row ring fits shared memory)
 };
 
 struct BmNorm {
@@ -173,6 +174,7 @@ bool sweep_s8_ok(const mvsv_ctx* c, const SweepPlan& p);
 cudaError_t launch_sweep(mvsv_ctx* c, int B, const SweepPlan& p, int bottomUp, bool s8);
 int sgbm_choose_td_cluster(mvsv_ctx* c);
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF);
+bool sgbm_vsum_wide(const SgbmNorm& n);
 
 #ifdef __CUDACC__
 // ---- packed 16x2 helpers -----------------------------------------------------------------------------

@@ -128,9 +128,11 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 constexpr int VS_RD = 4;       // raw-ring depth of the cost kernel's producer (rows in flight + 1)
 
-// geometry fixed by G: entries a CTA can touch, 8-entry vectors per channel, producer warps
-template <int G> struct VsGeom {
-    static constexpr int CT = vs_compute_threads(G);
+// geometry fixed by G: entries a CTA can touch, 8-entry vectors per channel, producer warps.  WIDE (G = 32, D > 128
+// only): 768 compute threads = 24 columns per CTA instead of 16, when the row ring still fits shared memory -- the
+// 271 staged entries per row are then shared by more columns (cfg 4: 8.14 -> 7.3 ms per 14 frames).
+template <int G, bool WIDE> struct VsGeom {
+    static constexpr int CT = (WIDE && G == 32) ? 768 : vs_compute_threads(G);
     static constexpr int PX = CT / G;
     static constexpr int NE = PX - 1 + 8 * G;
     static constexpr int NV = (NE + 2 + 7) / 8;                // one spare entry pair for the odd copies
@@ -145,10 +147,10 @@ template <int G> struct VsGeom {
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int G, bool R8, bool BANDS>
-__global__ void __launch_bounds__(VsGeom<G>::THREADS) k_sgbm_vsum(VsArgs a)
+template <int G, bool R8, bool BANDS, bool WIDE>
+__global__ void __launch_bounds__(VsGeom<G, WIDE>::THREADS) k_sgbm_vsum(VsArgs a)
 {
-    using GE = VsGeom<G>;
+    using GE = VsGeom<G, WIDE>;
     constexpr int PX = GE::PX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: sR[2 buf][6][8][LEN] u16 | sL[2 buf][PX][12] u32 | ring[bs][CT] (uint2 if the pixel cost
@@ -681,6 +683,16 @@ __global__ void k_fill_i16(int16_t* p, size_t n, int16_t v)
     if (i < n) p[i] = v;
 }
 
+// dynamic shared memory of the cost kernel (see its layout comment)
+template <int G, bool WIDE>
+size_t vsum_smem_bytes(int bs, bool r8)
+{
+    using GE = VsGeom<G, WIDE>;
+    const int LEN = 8 * GE::NV + 8;
+    return (size_t)2 * 6 * 8 * LEN * 2 + (size_t)2 * GE::PX * 12 * 4 + (size_t)bs * GE::CT * (r8 ? 8 : 16) +
+           (size_t)VS_RD * GE::IPL * 2 * GE::NPT * 16 + (size_t)VS_RD * GE::RPL * GE::NPT * 8;
+}
+
 template <int G, bool PAD>
 void launch_sgbm_g(mvsv_ctx* c, int B)
 {
@@ -694,17 +706,16 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
                                               planeStrideR, c->vsRP, c->vsJOFF);
     }
     std::function<void(int, int)> launch_vsum;
-    {
-        constexpr int PX = VsGeom<G>::PX;
+    auto make_vsum = [&](auto wideTag) {
+        constexpr bool WIDE = decltype(wideTag)::value;
+        using GE = VsGeom<G, WIDE>;
+        constexpr int PX = GE::PX;
         VsArgs a;
         a.recL = c->recL; a.plR = c->plR; a.planeStrideR = planeStrideR;
         a.VS = c->VS; a.W = c->W; a.H = c->H; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.minD = n.minD; a.minX1 = n.minX1;
         a.SH2 = n.SH2; a.NV = c->vsNV; a.LEN = 8 * c->vsNV + 8; a.RP = c->vsRP; a.JOFF = c->vsJOFF;
         const bool r8 = 2 * n.ftzero + 63 <= 255;
-        using GE = VsGeom<G>;
-        const size_t smem = (size_t)2 * 6 * 8 * a.LEN * 2 + (size_t)2 * PX * 12 * 4 +
-                            (size_t)(2 * n.SH2 + 1) * GE::CT * (r8 ? 8 : 16) +
-                            (size_t)VS_RD * GE::IPL * 2 * GE::NPT * 16 + (size_t)VS_RD * GE::RPL * GE::NPT * 8;
+        const size_t smem = vsum_smem_bytes<G, WIDE>(2 * n.SH2 + 1, r8);
         // small batches: split the rows into bands until the grid covers the SMs (each band repeats bs-1 rows)
         const int gx = (n.W1 + PX - 1) / PX, bs = 2 * n.SH2 + 1;
         int bands = 1;
@@ -716,13 +727,19 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
             dim3 grd(gx, nb, (c->H + v.bandRows - 1) / v.bandRows);
             KernelTimer kt(c, KID_SGBM_VSUM);
             if (bands > 1) {
-                if (r8) k_sgbm_vsum<G, true, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
-                else k_sgbm_vsum<G, false, true><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+                if (r8) k_sgbm_vsum<G, true, true, WIDE><<<grd, GE::THREADS, smem, st>>>(v);
+                else k_sgbm_vsum<G, false, true, WIDE><<<grd, GE::THREADS, smem, st>>>(v);
             } else {
-                if (r8) k_sgbm_vsum<G, true, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
-                else k_sgbm_vsum<G, false, false><<<grd, VsGeom<G>::THREADS, smem, st>>>(v);
+                if (r8) k_sgbm_vsum<G, true, false, WIDE><<<grd, GE::THREADS, smem, st>>>(v);
+                else k_sgbm_vsum<G, false, false, WIDE><<<grd, GE::THREADS, smem, st>>>(v);
             }
         };
+    };
+    if constexpr (G == 32) {
+        if (n.vsWide) make_vsum(std::true_type());
+        else make_vsum(std::false_type());
+    } else {
+        make_vsum(std::false_type());
     }
     AggArgs a;
     a.VS = c->VS; a.C = c->C; a.S = c->S; a.H = c->H; a.W = c->W; a.W1 = n.W1; a.D = n.D; a.Dp = n.Dp; a.SW2 = n.SW2;
@@ -776,14 +793,24 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
 template <int G>
 cudaError_t cfg_vsum()
 {
-    cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
+    if constexpr (G == 32) {
+        e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_vsum<G, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_sgbm_vsum<G, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(k_sgbm_h1<G, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_sgbm_h1<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -821,9 +848,16 @@ int sgbm_choose_td_cluster(mvsv_ctx* c)
 }
 
 // Geometry of the reversed right-image planes for the cost kernel (see k_sgbm_prefilter / k_sgbm_vsum).
+// 768 compute threads for the cost kernel at D > 128 when its shared memory still fits (k_sgbm_vsum, VsGeom)
+bool sgbm_vsum_wide(const SgbmNorm& n)
+{
+    if (n.G != 32) return false;
+    return vsum_smem_bytes<32, true>(2 * n.SH2 + 1, 2 * n.ftzero + 63 <= 255) <= (size_t)200 * 1024;
+}
+
 void sgbm_plane_geometry(const SgbmNorm& n, int W, int* NV, int* RP, int* JOFF)
 {
-    const int PX = vs_compute_threads(n.G) / n.G;
+    const int PX = (n.vsWide ? 768 : vs_compute_threads(n.G)) / n.G;
     const int NE = PX - 1 + 8 * n.G;                 // entries a CTA can touch (== VsGeom<G>::NE)
     const int nv = (NE + 2 + 7) / 8;                 // == VsGeom<G>::NV
     const int K = W - PX - n.minX1 + n.minD;         // j0 = JOFF + K - xa must be a multiple of 8 (xa is)
