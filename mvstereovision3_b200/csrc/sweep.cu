@@ -325,7 +325,6 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         unsigned Cc[NR];
         lds_block<NR>(Cc, stgC + ((size_t)st * nthr + tid) * LBW);
         __syncwarp();
-        issueC(t + NSTG, row_off(fi + NSTG / a.H, yi, NSTG % a.H));
 
         unsigned Ss[NR];                              // sum of the three paths of this row
         // tag of the records received in this row / sent for the next one: 4 bits in the free top bits of the first
@@ -416,7 +415,10 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
 
         // ---- diagonal from x-1 first: it feeds the warp / strip to the right
         diag(std::integral_constant<int, 0>(), Ss);
-        // ---- S of row t + NSTG - 1 into the stage whose write-back (row t - 1) has been read out
+        // ---- prefetches, issued after the first diagonal so that its border record does not queue behind them:
+        //      C of row t + NSTG into the stage just read; S of row t + NSTG - 1 into the stage whose write-back (row
+        //      t - 1) has been read out
+        issueC(t + NSTG, row_off(fi + NSTG / a.H, yi, NSTG % a.H));
         issueS(t + NSTG - 1, row_off(fi + (NSTG - 1) / a.H, yi, (NSTG - 1) % a.H));
         // ---- vertical path: state in registers
         if (firstRow) reset_path<NR, G, PAD>(Lv, mv, q, jpad);
