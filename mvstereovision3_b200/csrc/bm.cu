@@ -93,16 +93,18 @@ __device__ __forceinline__ void bm_acc(unsigned (&acc)[4], const uint2& e, const
 
 // The absolute differences of the last blockSize rows stay in a per-thread shared-memory ring (8 bytes per row), so
 // the row that leaves the window is not evaluated a second time.
-template <int G>
+// Threads are numbered (column, octet) with exactly D / 8 octets per column -- not a power of two as in the row scans, so
+// no lane idles at D = 80 -- and consecutive threads store consecutive 16-byte pieces of the volume.
 __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ preL, const uint8_t* __restrict__ preR,
                                                    size_t pitch, int H, int width1, int D, int lofs, int w2,
                                                    uint16_t* __restrict__ col)
 {
     extern __shared__ uint2 bm_ring[];          // [bs][128]
-    const int Dp = D;           // pixel stride of the column-sum volume: numDisp (a multiple of 16); idle lanes store nothing
+    const int Dp = D;           // pixel stride of the column-sum volume: numDisp (a multiple of 16)
+    const int nOct = D >> 3;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int xp = gtid / G, q = gtid % G;
-    if (xp >= width1 || q * 8 >= D) return;
+    const int xp = gtid / nOct, q = gtid - xp * nOct;
+    if (xp >= width1) return;
     const size_t fo = (size_t)blockIdx.y * H * pitch;
     const uint8_t* pl = preL + fo + xp + lofs;
     const size_t ra = fo + xp + q * 8;                       // byte address of R[.][x' + 8q]
@@ -144,20 +146,23 @@ struct BmArgs {
     int W, H, width1, D, Dp, lofs, w2, texThr, uniq, B;
 };
 
-template <int G>
+// Lanes are numbered (row, octet) with exactly nOct = D / 8 octets per row -- 10 at bm.yml, so a warp holds three rows
+// (30 lanes) instead of two rows in two power-of-two groups of 16 with 6 idle lanes each.  The minimum over a row's
+// lanes is a shfl_down ladder bounded by the segment, then a broadcast from the segment's first lane.
 __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
 {
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nOct = a.D >> 3, RW = 32 / nOct;                 // octets per row, rows per warp
+    const int lane = threadIdx.x & 31, rw = lane / nOct, q = lane - rw * nOct;
     const int vrows = a.H - 2 * a.w2;
     const long long nrows = (long long)a.B * vrows;
-    long long r = gtid / G;
-    const int q = (int)(gtid % G);
-    const bool active = r < nrows;
-    if (!active) r = nrows - 1;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long r = warp * RW + rw;
+    const bool active = rw < RW && r < nrows;
+    if (r >= nrows) r = nrows - 1;
+    const int base = min(rw, RW - 1) * nOct;                   // first lane of this row's segment
     const int f = (int)(r / vrows), y = (int)(r % vrows) + a.w2;
-    const bool mem = q * 8 < a.D;               // lanes beyond numDisp hold no disparity: no loads, keys stay "infinite"
-    const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + (mem ? q * 8 : 0);
-    const uint16_t* cp = a.col + rowBase;
+    const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + q * 8;
+    const uint16_t* cp = a.col + (rw < RW ? rowBase : 0);
     const size_t outRow = ((size_t)f * a.H + y) * a.W;
     const int bs = 2 * a.w2 + 1;
     const unsigned kb = (unsigned)q * 8u;
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
         const uint4 v = ld128(cp + (size_t)j * a.Dp);
         hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
     }
-    // The per-pixel epilogue (texture test, sub-pixel division, store) is identical on the G lanes of a pixel, so it is
-    // deferred: lane q keeps the winner of every G-th step and the G lanes finish G pixels at once.
+    // The per-pixel epilogue (texture test, sub-pixel division, store) is identical on the lanes of a row, so it is
+    // deferred: lane q keeps the winner of every nOct-th step and the lanes of a row finish nOct pixels at once.
     unsigned svKey = 0, svP = 0, svN = 0;
     int svX = -1, sc = 0;
     auto flush = [&]() {
@@ -191,9 +196,12 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
         key = __vimin3_u32(key, (Sf[1] & 0xffff0000u) | (kb + 3), (Sf[2] << 16) + (kb + 4));
         key = __vimin3_u32(key, (Sf[2] & 0xffff0000u) | (kb + 5), (Sf[3] << 16) + (kb + 6));
         key = min(key, (Sf[3] & 0xffff0000u) | (kb + 7));
-        if (!mem) key = 0xffffffffu;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned other = __shfl_down_sync(FULL, key, o);
+            if (q + o < nOct) key = min(key, other);
+        }
+        key = __shfl_sync(FULL, key, base);
         const int minsad = (int)(key >> 16), mind = (int)(key & 0xffffu);
         bool reject = false;
         if (a.uniq > 0) {
@@ -203,21 +211,19 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
             for (int j = 0; j < 8; ++j) {
                 const int k = (int)kb + j;
                 const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
-                bad |= (k < a.D) && (k < mind - 1 || k > mind + 1) && (s <= thresh);
+                bad |= (k < mind - 1 || k > mind + 1) && (s <= thresh);
             }
-            const unsigned bal = __ballot_sync(FULL, bad);
-            const unsigned gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+            const unsigned bal = __ballot_sync(FULL, bad && rw < RW);
+            const unsigned gmask = (nOct == 32) ? FULL : (((1u << nOct) - 1u) << base);
             reject = (bal & gmask) != 0u;
         }
         const int ip = (mind + 1 < a.D) ? mind + 1 : a.D - 2;
         const int in = (mind > 0) ? mind - 1 : 1;
         unsigned vp = pick16b(Sf, ip & 7), vn = pick16b(Sf, in & 7);
-        if (G > 1) {
-            vp = __shfl_sync(FULL, vp, ip >> 3, G);
-            vn = __shfl_sync(FULL, vn, in >> 3, G);
-        }
+        vp = __shfl_sync(FULL, vp, base + (ip >> 3));
+        vn = __shfl_sync(FULL, vn, base + (in >> 3));
         if (sc == q) { svKey = key; svP = vp; svN = vn; svX = reject ? -1 : xp + a.lofs; }
-        if (++sc == G) { flush(); sc = 0; }
+        if (++sc == nOct) { flush(); sc = 0; }
         if (xp + 1 < xEnd) {
             const uint4 nx = ld128(cp + (size_t)(xp + 1 + a.w2) * a.Dp);
             const uint4 od = ld128(cp + (size_t)(xp - a.w2) * a.Dp);
@@ -231,13 +237,6 @@ __global__ void k_fill16(int16_t* p, size_t n, int16_t v)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-
-template <int G>
-void launch_wta(mvsv_ctx* c, const BmArgs& a, int B)
-{
-    const long long threads = (long long)B * (c->H - 2 * a.w2) * G;
-    k_bm_wta<G><<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(a);
 }
 
 }  // namespace
@@ -262,37 +261,23 @@ void launch_bm(mvsv_ctx* c, int B)
         { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2); }
     }
     {
-        const long long threads = (long long)n.width1 * n.G;
+        const long long threads = (long long)n.width1 * (n.D / 8);
         dim3 grd((unsigned)((threads + 127) / 128), B);
         // blockSize^2 * 2 * cap <= 65535 (contract) bounds blockSize by 181: the ring needs at most 181 KB
         const size_t ringBytes = (size_t)n.bs * 128 * sizeof(uint2);
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(k_bm_colsum<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_bm_colsum<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_bm_colsum<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_bm_colsum<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaFuncSetAttribute(k_bm_colsum<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             configured = true;
         }
         KernelTimer kt(c, KID_BM_COLSUM);
-        switch (n.G) {
-            case 2: k_bm_colsum<2><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 4: k_bm_colsum<4><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 8: k_bm_colsum<8><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            case 16: k_bm_colsum<16><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-            default: k_bm_colsum<32><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col); break;
-        }
+        k_bm_colsum<<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col);
     }
     BmArgs a;
     a.col = c->bm_col; a.tex = c->bm_tex2; a.disp = c->disp; a.W = W; a.H = H; a.width1 = n.width1; a.D = n.D; a.Dp = n.Dp;
     a.lofs = n.lofs; a.w2 = n.w2; a.texThr = n.tex; a.uniq = n.uniq; a.B = B;
     KernelTimer kt(c, KID_BM_WTA);
-    switch (n.G) {
-        case 2: launch_wta<2>(c, a, B); break;
-        case 4: launch_wta<4>(c, a, B); break;
-        case 8: launch_wta<8>(c, a, B); break;
-        case 16: launch_wta<16>(c, a, B); break;
-        default: launch_wta<32>(c, a, B); break;
-    }
+    const int rowsPerWarp = 32 / (n.D / 8);
+    const long long warps = ((long long)B * (H - 2 * n.w2) + rowsPerWarp - 1) / rowsPerWarp;
+    k_bm_wta<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(a);
 }
