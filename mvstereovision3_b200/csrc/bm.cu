@@ -265,10 +265,10 @@ void launch_bm(mvsv_ctx* c, int B)
         dim3 grd((unsigned)((threads + 127) / 128), B);
         // blockSize^2 * 2 * cap <= 65535 (contract) bounds blockSize by 181: the ring needs at most 181 KB
         const size_t ringBytes = (size_t)n.bs * 128 * sizeof(uint2);
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[64] = {};        // per device: a process may drive several GPUs
+        if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
             cudaFuncSetAttribute(k_bm_colsum, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            configured = true;
+            if (c->device >= 0 && c->device < 64) configured[c->device] = true;
         }
         KernelTimer kt(c, KID_BM_COLSUM);
         k_bm_colsum<<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col);

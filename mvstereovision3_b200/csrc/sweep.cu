@@ -482,11 +482,14 @@ size_t sweep_smem_bytes(int NR, int G, int Mmax, int nthr)
 template <int NR, int G, bool PAD, int MODE, bool DSM>
 cudaError_t launch_one(const SweepArgs& a, int nthr, size_t smem, cudaStream_t st, bool* fits)
 {
-    static bool configured = false;
-    if (!configured) {
+    // function attributes are per device: a process may drive several GPUs with one engine each
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep<NR, G, PAD, MODE, DSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_LIMIT);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(a.NS * a.NF, 1, 1); cfg.blockDim = dim3(nthr, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;

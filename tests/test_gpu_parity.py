@@ -539,3 +539,30 @@ def test_byte_form_of_S_equals_16bit_form(oracle, kw):
         for flags in (1, 3):
             check("S/%d/%d" % (flags, b), res[flags][1][b], Sv)
             check("disp/%d/%d" % (flags, b), res[flags][0][b], disp)
+
+
+def test_two_devices_in_one_process(oracle):
+    """One process, one engine per GPU: kernel attributes (dynamic shared memory of the sweep
+    and the StereoBM column sums) are configured per device.  Needs two GPUs; skipped otherwise."""
+    import ctypes
+    try:
+        rt = ctypes.CDLL("libcudart.so")
+    except OSError:
+        rt = None
+    n = ctypes.c_int(0)
+    if rt is None or rt.cudaGetDeviceCount(ctypes.byref(n)) != 0 or n.value < 2:
+        pytest.skip("needs two CUDA devices")
+    p = cases.sgbm_params(minDisp=1, numDisp=64, blockSize=9, speckleWindowSize=50, speckleRange=2)
+    bmp = dict(numDisp=32, blockSize=9, preFilterCap=31, uniquenessRatio=5, textureThreshold=10)
+    H, W = 60, 260
+    l, r, _ = synth.stereogram(H, W, 1, 64, seed=3)
+    want = oracle.sgbm(l, r, p)
+    want_bm = oracle.bm(l, r, bmp)
+    for dev in (1, 0, 1):
+        with api.Engine(W, H, max_batch=1, device=dev) as e:
+            e.set_sgbm_params(**gpu_params(p))
+            e.compute(l, r, api.STAGE_SGBM)
+            check("sgbm on device %d" % dev, e.download(1)["disp"][0], want)
+            e.set_bm_params(**bmp)
+            e.compute(l, r, api.STAGE_BM)
+            check("bm on device %d" % dev, e.download(1)["disp"][0], want_bm)
