@@ -566,3 +566,25 @@ def test_two_devices_in_one_process(oracle):
             e.set_bm_params(**bmp)
             e.compute(l, r, api.STAGE_BM)
             check("bm on device %d" % dev, e.download(1)["disp"][0], want_bm)
+
+
+@pytest.mark.parametrize("p,B", [(CFG2, 148), (CFG2_SHIPPED, 74)], ids=["cfg2_b148", "sgbm_yml_d128_b74"])
+def test_full_bench_batch_twins_agree(p, B):
+    """The bench batches at full size (every sweep CTA walks several frames, all SMs busy): the batch holds four distinct
+    pairs repeated, every copy must equal its twin on every repetition, and one copy of each must equal cv2.  This is the
+    configuration in which the frame-boundary pacing race of the sweep showed (tools/determinism_check.py)."""
+    cv2 = _cv2()
+    H, W = 480, 752
+    gen = [synth.stereogram(H, W, p["minDisp"], p["numDisp"], seed=50 + s)[:2] for s in range(4)]
+    L = np.stack([gen[b % 4][0] for b in range(B)])
+    R = np.stack([gen[b % 4][1] for b in range(B)])
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_sgbm_params(**gpu_params(p))
+        for it in range(3):
+            e.compute(L, R, api.STAGE_SGBM)
+            d = e.download(B)["disp"]
+            for b in range(4, B):
+                assert np.array_equal(d[b], d[b % 4]), "repetition %d: frame %d differs from its twin in %d pixels" % (
+                    it, b, int((d[b] != d[b % 4]).sum()))
+    for s in range(4):
+        check("vs cv2 / %d" % s, d[s], _cv_sgbm(cv2, gen[s][0], gen[s][1], p))
