@@ -166,6 +166,56 @@ __device__ __forceinline__ void path_step(unsigned (&L)[NR], unsigned& mm, const
     mm = __vminu2(mv, __byte_perm(mv, 0, 0x1032));
 }
 
+// Two independent recurrence steps (two paths of the same pixel: same C, separate state) in one loop body, so that the
+// two dependency chains interleave and a warp has twice the independent instructions in flight.
+template <int NR, int G, bool PAD>
+__device__ __forceinline__ void path_step2(unsigned (&L)[NR], unsigned& mm, unsigned (&K)[NR], unsigned& km, const unsigned (&C)[NR],
+                                           unsigned P1P1, unsigned P2P2, unsigned one, int q, int jpad)
+{
+    unsigned upL = 0xffffffffu, dnL = 0xffffffffu, upK = 0xffffffffu, dnK = 0xffffffffu;
+    unsigned PjL = L[0] * one + P1P1, PjK = K[0] * one + P1P1;
+    if (G > 1) {
+        const unsigned uL = __shfl_up_sync(FULL, L[NR - 1] * one + P1P1, 1, G), uK = __shfl_up_sync(FULL, K[NR - 1] * one + P1P1, 1, G);
+        const unsigned dL = __shfl_down_sync(FULL, PjL, 1, G), dK = __shfl_down_sync(FULL, PjK, 1, G);
+        if (q != 0) { upL = uL; upK = uK; }
+        if (q != G - 1) { dnL = dL; dnK = dK; }
+    }
+    const unsigned mP2L = mm + P2P2, negL = 0u - mm, mP2K = km + P2P2, negK = 0u - km;
+    unsigned XjL = __byte_perm(upL, PjL, 0x5432), XjK = __byte_perm(upK, PjK, 0x5432);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+        const unsigned PnL = (j + 1 < NR) ? L[j + 1] * one + P1P1 : dnL;
+        const unsigned PnK = (j + 1 < NR) ? K[j + 1] * one + P1P1 : dnK;
+        const unsigned XnL = __byte_perm(PjL, PnL, 0x5432), XnK = __byte_perm(PjK, PnK, 0x5432);
+        unsigned nL = (__vimin3_u16x2(XjL, XnL, __vminu2(L[j], mP2L)) * one + negL) * one + C[j];
+        unsigned nK = (__vimin3_u16x2(XjK, XnK, __vminu2(K[j], mP2K)) * one + negK) * one + C[j];
+        if (PAD && q == G - 1 && j >= jpad) { nL = MVSV_PK_MAX; nK = MVSV_PK_MAX; }
+        L[j] = nL; K[j] = nK;
+        XjL = XnL; PjL = PnL; XjK = XnK; PjK = PnK;
+    }
+    unsigned a0 = L[0], a1 = L[1], a2 = L[2], a3 = L[3], b0 = K[0], b1 = K[1], b2 = K[2], b3 = K[3];
+#pragma unroll
+    for (int j = 4; j < NR; j += 8) {
+        if (j + 7 < NR) {
+            a0 = __vimin3_u16x2(a0, L[j], L[j + 4]); a1 = __vimin3_u16x2(a1, L[j + 1], L[j + 5]);
+            a2 = __vimin3_u16x2(a2, L[j + 2], L[j + 6]); a3 = __vimin3_u16x2(a3, L[j + 3], L[j + 7]);
+            b0 = __vimin3_u16x2(b0, K[j], K[j + 4]); b1 = __vimin3_u16x2(b1, K[j + 1], K[j + 5]);
+            b2 = __vimin3_u16x2(b2, K[j + 2], K[j + 6]); b3 = __vimin3_u16x2(b3, K[j + 3], K[j + 7]);
+        } else {
+            a0 = __vminu2(a0, L[j]); a1 = __vminu2(a1, L[j + 1]); a2 = __vminu2(a2, L[j + 2]); a3 = __vminu2(a3, L[j + 3]);
+            b0 = __vminu2(b0, K[j]); b1 = __vminu2(b1, K[j + 1]); b2 = __vminu2(b2, K[j + 2]); b3 = __vminu2(b3, K[j + 3]);
+        }
+    }
+    unsigned mvL = __vimin3_u16x2(a0, a1, __vminu2(a2, a3)), mvK = __vimin3_u16x2(b0, b1, __vminu2(b2, b3));
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        mvL = __vminu2(mvL, __shfl_xor_sync(FULL, mvL, o, G));
+        mvK = __vminu2(mvK, __shfl_xor_sync(FULL, mvK, o, G));
+    }
+    mm = __vminu2(mvL, __byte_perm(mvL, 0, 0x1032));
+    km = __vminu2(mvK, __byte_perm(mvK, 0, 0x1032));
+}
+
 template <int NR, int G, bool PAD>
 __device__ __forceinline__ void reset_path(unsigned (&L)[NR], unsigned& mm, int q, int jpad)
 {
@@ -335,8 +385,9 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
 
         // One diagonal path.  DIR 0: predecessor (x-1, previous row), state flows to the right; DIR 1: predecessor
         // (x+1, previous row), state flows to the left.  The result is left in L.
-        auto diag = [&](auto dirTag, unsigned (&L)[NR]) {
+        auto diag = [&](auto dirTag, auto fuseTag, unsigned (&L)[NR]) {
             constexpr int DIR = decltype(dirTag)::value;
+            constexpr bool FUSE_V = decltype(fuseTag)::value;    // run the vertical path's step interleaved with this one
             const int sidx = DIR ? s2 : s1;
             unsigned* const slot = (DIR ? st2 : st1) + (size_t)(sidx * G + q) * LBW;
             unsigned* const mArr = DIR ? m2 : m1;
@@ -388,7 +439,12 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
                 lds_block<NR>(L, slot);
                 mm = mArr[sidx];
             }
-            path_step<NR, G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, one, q, jpad);
+            if (FUSE_V) {
+                if (firstRow) reset_path<NR, G, PAD>(Lv, mv, q, jpad);
+                path_step2<NR, G, PAD>(L, mm, Lv, mv, Cc, a.P1P1, a.P2P2, one, q, jpad);
+            } else {
+                path_step<NR, G, PAD>(L, mm, Cc, a.P1P1, a.P2P2, one, q, jpad);
+            }
             if (act) {
                 sts_block<NR>(slot, L);
                 if (q == 0) mArr[sidx] = mm;
@@ -414,21 +470,19 @@ __global__ void __launch_bounds__(SW_MAX_THREADS, 1) k_sweep(SweepArgs a)
         };
 
         // ---- diagonal from x-1 first: it feeds the warp / strip to the right
-        diag(std::integral_constant<int, 0>(), Ss);
+        diag(std::integral_constant<int, 0>(), std::true_type(), Ss);
         // ---- prefetches, issued after the first diagonal so that its border record does not queue behind them:
         //      C of row t + NSTG into the stage just read; S of row t + NSTG - 1 into the stage whose write-back (row
         //      t - 1) has been read out
         issueC(t + NSTG, row_off(fi + NSTG / a.H, yi, NSTG % a.H));
         issueS(t + NSTG - 1, row_off(fi + (NSTG - 1) / a.H, yi, (NSTG - 1) % a.H));
-        // ---- vertical path: state in registers
-        if (firstRow) reset_path<NR, G, PAD>(Lv, mv, q, jpad);
-        path_step<NR, G, PAD>(Lv, mv, Cc, a.P1P1, a.P2P2, one, q, jpad);
+        // ---- vertical path (state in registers): its step ran interleaved with the first diagonal's
 #pragma unroll
         for (int j = 0; j < NR; ++j) Ss[j] = FAST ? Ss[j] * one + Lv[j] : __viaddmin_u16x2(Ss[j], Lv[j], MVSV_PK_MAX);
         // ---- diagonal from x+1 last: it needs the warp / strip to the right
         {
             unsigned L[NR];
-            diag(std::integral_constant<int, 1>(), L);
+            diag(std::integral_constant<int, 1>(), std::false_type(), L);
 #pragma unroll
             for (int j = 0; j < NR; ++j) Ss[j] = FAST ? Ss[j] * one + L[j] : __viaddmin_u16x2(Ss[j], L[j], MVSV_PK_MAX);
         }
