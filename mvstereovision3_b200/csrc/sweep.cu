@@ -18,15 +18,20 @@
 // each warp publishes a per-path progress counter in shared memory and its neighbour polls it.  The ring has nw
 // spare slots because warps may drift by one row per warp boundary.
 //
-// Strip borders cross CTAs through global memory (L2) without flags or fences: path costs are at most 0x7fff, so
-// bit 15 of every 16-bit value is free; the sender ORs a 4-bit sequence number of the row into those bits of each
-// 8-byte half of a 16-byte chunk, and the receiver polls the (four-deep) record itself until every chunk
-// carries the number it expects (the low-latency protocol of collective libraries).  With a release/acquire
-// flag the hand-off cost 3.6-4 us per hop and set the pace of the whole frame; with tagged data it is one L2 round
-// trip.  The warp that owns a strip's first pixel runs its paths in the order (x+1 diagonal, vertical, x-1
-// diagonal) and all others (x-1, vertical, x+1): what a neighbouring strip needs is produced first and what comes
-// from it is consumed last, which leaves 4/3 of a row time for the hand-off.
-// All CTAs of a frame are co-resident by construction (cooperative launch, one CTA per SM).
+// Path order inside a row is (diagonal from x-1, fused with the vertical path in one loop body: two independent
+// dependency chains) -> (diagonal from x+1): what a neighbour needs first is produced first and what comes from a
+// neighbour is consumed last.  (Giving the warp with a strip's first pixel the opposite order -- more slack per border
+// on paper -- was measured and rejected: DESIGN.md section 8.)
+//
+// Strip borders cross CTAs without flags or fences: path costs are at most 0x7fff, so bit 15 of every 16-bit value
+// is free; the sender ORs a 4-bit sequence number of the row into those bits of each 8-byte half of a 16-byte chunk,
+// and the receiver polls the (four-deep) record itself until every chunk carries the number it expects (the
+// low-latency protocol of collective libraries).  With a release/acquire flag the hand-off through global memory
+// cost 3.6-4 us per hop and set the pace of the whole frame; with tagged data it is one L2 round trip.  Two
+// transports: for one lane per pixel and 2..8 strips the strips of a frame are launched as one thread-block cluster
+// and the record is stored straight into the neighbour's shared memory (mapa + st.shared::cluster; template
+// parameter DSM); otherwise it goes through global memory (L2) and all CTAs are co-resident by a cooperative launch
+// (one CTA per SM).
 //
 // Operands: a warp's 32/G pixels of a row are one contiguous span of C (and S).  The warp copies it with coalesced
 // 16-byte cp.async (LDGSTS) straight into shared memory, transposing on the way: chunk c of the span lands in the
@@ -44,7 +49,7 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int SW_MAX_THREADS = 352;          // 11 warps: 65536 / 352 = 186 registers per thread
+constexpr int SW_MAX_THREADS = 352;          // 11 warps = 3 per scheduler: 168 registers per thread
 constexpr int SW_SMEM_LIMIT = 227 * 1024;
 
 struct SweepArgs {
