@@ -1,15 +1,19 @@
 // StereoSGBM on sm_100a -- replaces cv::StereoSGBM::compute behind Disparity::sgbm
 // (reference src/disparity.cpp:6-10).  Stage semantics: SURVEY.md Appendix A.2 (pinned against cv2 4.13).
+// This file: prefilter, cost kernel, the two row scans (+ WTA) and the launch sequence; the fused previous-row sweep
+// lives in sweep.cu.
 //
-// Data layout in HBM (all volumes int16, disparity innermost, padded to Dp = 8*G so that one pixel's
-// disparities are G consecutive 16-byte vectors):
-//   planes[img][6][B][H][pitch] u8  : prefilter channels a/lo/hi for the clipped x-Sobel and the raw image
-//   VS[B][H][W1][Dp]                : vertical box sums of the Birchfield-Tomasi pixel cost
-//   C [B][H][W1][Dp]                : block cost (horizontal box sum of VS)
-//   S [B][H][W1][Dp]                : sum of path costs L_r
-// Lane mapping everywhere: a pixel's D disparities are spread over G = Dp/8 adjacent lanes, 8 disparities
-// (four packed u16x2 registers) per lane; the min over d is a width-G shuffle butterfly; all arithmetic is
-// packed 16x2 (VIADD.16x2 / VIMNMX.U16x2 / VIMNMX3 / VIADDMNMX -- the DPX path on sm_100a).
+// Data layout in HBM (volumes: disparity innermost, pixel stride Dp = numDisp rounded up to 8 / 16 / 32 for
+// D <= 64 / 128 / 256):
+//   recL[B][H][W] 8-byte records, plR[6][B][H][RP] u16 : prefilter channels a/lo/hi of the clipped x-Sobel and the raw image
+//   VS[B][H][W1][Dp] u16            : vertical box sums of the Birchfield-Tomasi pixel cost
+//   C [B][H][W1][Dp] u16            : block cost (horizontal box sum of VS)
+//   S [B][H][W1][Dp] u16 or u8      : sum of path costs L_r -- as one byte per cell (the paths' excess over npaths * C)
+//                                     while npaths * P2 <= 255 ("S8", see sweep.cu / DESIGN.md section 3)
+// Lane mapping of the kernels in this file: a pixel's disparities are spread over G adjacent lanes (G = next power of
+// two >= Dp / 8), 8 disparities (four packed u16x2 registers) per lane; lanes beyond Dp hold padding and never touch
+// memory; the min over d is a width-G shuffle butterfly; all arithmetic is packed 16x2 (VIADD / VIMNMX.U16x2 /
+// VIMNMX3 / VIADDMNMX on the integer ALU pipe of sm_100a).
 #include "mvsv_internal.h"
 
 #include <algorithm>

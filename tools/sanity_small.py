@@ -1,5 +1,5 @@
-"""Tiny invocation of every kernel of the path (for compute-sanitizer): SGBM 5/8 paths through the fused cluster
-sweep and through the independent passes, padded D, BM, rectification, XYZ, ROI means, min/max."""
+"""Tiny invocation of every kernel of the path (for compute-sanitizer): SGBM 5/8 paths through the fused strip
+sweep (one, two and four lanes per pixel, cluster and global-memory border hand-off) and through the independent passes, padded D, BM, rectification, XYZ, ROI means, min/max."""
 import os
 import sys
 
