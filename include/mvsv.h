@@ -193,7 +193,8 @@ int mvsv_host_free(void* p);
  * (roi_h x roi_w int32 pairs: x*32, y*32 rounded).  Returns bytes written or a negative error. */
 /* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
  * bit 1: never keep the aggregated volume as bytes (mvsv_info.sgbm_s8).
- * bits 8..15: force the number of column strips per frame of the fused sweep (0xff = force the independent passes). */
+ * bits 8..15: force the number of column strips per frame of the fused sweep (0xff = force the independent passes,
+ * 0xfe = force the sweep with the usual choice of strips: small batches otherwise take the independent passes). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
 long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
 

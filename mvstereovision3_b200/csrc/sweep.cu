@@ -620,7 +620,8 @@ void sweep_layout(int D, int* G, int* NR)
 }
 
 // Chooses the strip decomposition for a batch of B frames: NS strips per frame (0 = the sweep cannot run: use the
-// independent passes), NF frames in flight, CTA size.  `forcedNS` > 0 pins the strip count (test hook).
+// independent passes), NF frames in flight, CTA size.  `forcedNS` > 0 pins the strip count, 0xfe only rules out the
+// independent passes (test hooks).
 void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p)
 {
     const SgbmNorm& n = c->sg;
@@ -631,12 +632,13 @@ void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p)
     if (G * 2 * NR != n.Dp) return;                   // volumes are laid out with another pixel stride
     const int capThreads = SW_MAX_THREADS / 32 * 32;
     // Time model (measured on B200, profiles/r02_sweep_row_time.txt): a CTA's row takes about c0 + c1 * warps -- a
-    // latency floor plus the warps' share of the SM -- and a batch takes waves * H rows, waves = ceil(B / NF).
-    // Fewer, wider strips amortise the floor; more strips keep the frames of a small batch in one wave.
-    const double c0 = 1.1, c1 = 0.2;
+    // latency floor plus the warps' share of the SM -- plus the border hand-off when a frame has several strips
+    // (~0.5 us through a cluster's shared memory, ~1.6 us through global memory), and a batch takes waves * H rows,
+    // waves = ceil(B / NF).  Fewer, wider strips amortise the floor; more strips keep a small batch in one wave.
+    const double c0 = 1.1, c1 = 0.2, hoCluster = 0.5, hoGlobal = 1.6;
     double best = 1e300;
     for (int NS = 1; NS <= std::min(n.W1, c->num_sms); ++NS) {
-        if (forcedNS > 0 && NS != forcedNS) continue;
+        if (forcedNS > 0 && forcedNS != 0xfe && NS != forcedNS) continue;
         const int Mmax = (n.W1 + NS - 1) / NS;
         const int nthr = (Mmax * G + 31) / 32 * 32;
         if (nthr > capThreads) continue;
@@ -644,10 +646,20 @@ void sweep_plan(const mvsv_ctx* c, int B, int forcedNS, SweepPlan* p)
         if (smem > (size_t)SW_SMEM_LIMIT) continue;
         const int NF = std::min(B, c->num_sms / NS);
         const int waves = (B + NF - 1) / NF;
-        const double cost = waves * (c0 + c1 * (nthr / 32)) + 1e-6 * NS;   // ties: fewer strips (less border traffic)
+        const double handoff = NS == 1 ? 0.0 : (G == 1 && NS <= 8 && NF * NS <= c->num_sms - 16) ? hoCluster : hoGlobal;
+        const double cost = waves * (c0 + c1 * (nthr / 32) + handoff) + 1e-6 * NS;   // us per row; ties: fewer strips
         if (cost < best) { best = cost; p->NS = NS; p->NF = NF; p->Mmax = Mmax; p->threads = nthr; p->smem = smem; }
     }
     p->G = G; p->NR = NR;
+    // Small batches: the three independent one-direction passes (k_sgbm_vdir: every column of every frame in parallel,
+    // 6 B/cell each at HBM speed plus ~0.1 ms of latency per pass) beat a sweep that is paced row by row -- a single
+    // 752x480 pair takes 0.4 ms that way and 1.1-2.5 ms in the sweep.  Not when the strip count is forced (tests).
+    if (p->NS > 0 && forcedNS <= 0) {        // forcedNS: a strip count, or 0xfe = "the sweep, strips chosen as usual"
+        const double sweepMs = best * c->H * 1e-3;
+        const double cells = (double)B * c->H * n.W1 * n.Dp;
+        const double vdirMs = 3.0 * (0.1 + cells * 6.0 / 5.5e12 * 1e3);
+        if (vdirMs < sweepMs) *p = SweepPlan();
+    }
 }
 
 size_t sweep_scratch_bytes(const mvsv_ctx* c)

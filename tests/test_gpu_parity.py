@@ -33,12 +33,15 @@ def check(name, got, want):
     assert np.array_equal(got, want), "%s: %s" % (name, first_diff(got, want))
 
 
+@pytest.mark.parametrize("sweep", [0, 0xfe], ids=["auto", "sweep"])
 @pytest.mark.parametrize("case", cases.SGBM_CASES, ids=[c[0] for c in cases.SGBM_CASES])
-def test_sgbm_stages_vs_oracle(oracle, golden, case):
+def test_sgbm_stages_vs_oracle(oracle, golden, case, sweep):
+    """Every stage against the oracle and the cv2 golden vectors.  "auto": the engine's own choice for a batch of two
+    (the independent one-direction passes); "sweep": the fused strip sweep the throughput configurations use."""
     name, p, H, W = case
     with api.Engine(W, H, max_batch=2) as e:
         e.set_sgbm_params(**gpu_params(p))
-        e.debug_set_flags(1)
+        e.debug_set_flags(1 | (sweep << 8))
         pair = [cases.sgbm_inputs(name, p, H, W, k) for k in ("ramp", "noise")]
         left = np.stack([pair[0][0], pair[1][0]])
         right = np.stack([pair[0][1], pair[1][1]])
@@ -526,7 +529,7 @@ def test_byte_form_of_S_equals_16bit_form(oracle, kw):
     for flags in (1, 3):
         with api.Engine(W, H, max_batch=2) as e:
             e.set_sgbm_params(**gpu_params(p))
-            e.debug_set_flags(flags)
+            e.debug_set_flags(flags | (0xfe << 8))          # the sweep also for this batch of two
             e.compute(L, R, api.STAGE_SGBM)
             res[flags] = (e.download(2)["disp"], e.debug_read(1, 2), e.info.sgbm_s8)
     bs = p["blockSize"] | 1

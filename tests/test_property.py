@@ -63,12 +63,18 @@ def test_cuda_vs_oracle_random(oracle, case):
     l, r = make_pair(p, H, W, seed, kind)
     gp = dict(p)
     gp["disparityMode"] = gp.pop("mode")
-    with api.Engine(W, H) as e:
-        e.set_sgbm_params(**gp)
-        e.compute(l, r, api.STAGE_SGBM)
-        got = e.download(1)["disp"][0]
     want = oracle.sgbm(l, r, p)
-    assert np.array_equal(got, want), (p, H, W, seed, kind, int((got != want).sum()))
+    # a single pair takes the independent one-direction passes by default; 0xfe forces the fused strip sweep the
+    # throughput configurations use (seed parity picks the number of strips: chosen by the engine, or 3)
+    for flags in (0, 0xfe << 8, 3 << 8):
+        if flags == (3 << 8) and seed % 2:
+            continue
+        with api.Engine(W, H) as e:
+            e.set_sgbm_params(**gp)
+            e.debug_set_flags(flags)
+            e.compute(l, r, api.STAGE_SGBM)
+            got = e.download(1)["disp"][0]
+        assert np.array_equal(got, want), (p, H, W, seed, kind, hex(flags), int((got != want).sum()))
 
 
 @pytest.mark.gpu
