@@ -8,9 +8,19 @@
 // fused in one row-marching kernel with the same 8-values-per-lane packed u16x2 layout as SGBM.
 #include "mvsv_internal.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Row-marching: a thread owns one column of BM_ROWS rows (an even count, so the row pairs of the reference's loop
 // never straddle two CTAs) and keeps the horizontal differences of the previous rows in registers.
@@ -134,103 +144,208 @@ __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ p
     }
 }
 
-__device__ __forceinline__ unsigned pick16b(const unsigned (&R)[4], int idx)
-{
-    const int w = (idx >> 1) & 3;
-    unsigned r = w == 0 ? R[0] : w == 1 ? R[1] : w == 2 ? R[2] : R[3];
-    return (idx & 1) ? (r >> 16) : (r & 0xffffu);
-}
-
 struct BmArgs {
     const uint16_t* col; const int* tex; int16_t* disp;
     int W, H, width1, D, Dp, lofs, w2, texThr, uniq, B;
 };
 
-// Lanes are numbered (row, octet) with exactly nOct = D / 8 octets per row -- 10 at bm.yml, so a warp holds three rows
-// (30 lanes) instead of two rows in two power-of-two groups of 16 with 6 idle lanes each.  The minimum over a row's
-// lanes is a shfl_down ladder bounded by the segment, then a broadcast from the segment's first lane.
-__global__ void __launch_bounds__(128) k_bm_wta(BmArgs a)
+// Winner-take-all over the horizontal window sums of `col`.  A row of the volume is scanned left to right by NL
+// adjacent lanes; lane q holds the octets q, q + NL, ... (OPL of them: 8 * OPL disparities in 4 * OPL packed registers)
+// of the running window sum, so the lanes of a row touch contiguous 16-byte pieces.  bm.yml (D = 80) runs with OPL = 2:
+// five lanes per row, six rows per warp.  Per step and lane: the first argmin through (SAD << 16) | k keys (one
+// shift-add or mask-or per value, 32-bit min3), a shfl_down ladder over the row's NL lanes, and the window update from
+// the column that enters and the one that leaves.
+//   RING: every column of the volume is read from HBM once.  A lane copies its pieces of column x + w2 + 1 + PF with
+//   cp.async into a private shared-memory ring of blockSize + 1 + PF slots and reads both the entering and the leaving
+//   column from there (without the ring the leaving column is a second HBM read 2 * w2 + 1 steps later: the rows in
+//   flight hold 230 MB of window at bm.yml, twice the L2 -- ncu: 14.5 GB of DRAM reads for a 7.1 GB volume).
+// The winner's neighbours S[mind -/+ 1] are read from a shared-memory copy of the row's sums (any lane of the row can
+// address any disparity there, no register indexing).  The per-pixel epilogue (texture test, sub-pixel division,
+// store) is identical on the lanes of a row, so it is deferred: lane q keeps the winner of every NL-th step and the
+// lanes of a row finish NL pixels at once; the texture value of a lane's pixel is requested one round ahead.
+constexpr int BM_PF = 3;       // columns in flight ahead of the window (RING)
+
+template <int OPL, bool RING>
+__global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sumsPerWarp)
 {
-    const int nOct = a.D >> 3, RW = 32 / nOct;                 // octets per row, rows per warp
-    const int lane = threadIdx.x & 31, rw = lane / nOct, q = lane - rw * nOct;
+    constexpr int NR = 4 * OPL;                                // packed registers per lane
+    extern __shared__ __align__(16) unsigned char bm_smem[];
+    // layout: sums[2 copies][4 warps][sumsPerWarp = RW rows x (D + 8), rounded up to 8] u16 | ring[slots][OPL][128 lanes] uint4
+    uint16_t* sums = reinterpret_cast<uint16_t*>(bm_smem);
+    uint4* ring = reinterpret_cast<uint4*>(bm_smem + (size_t)2 * 4 * sumsPerWarp * sizeof(uint16_t)) + threadIdx.x;
+    const int nOct = a.D >> 3, NL = nOct / OPL, RW = 32 / NL;  // lanes per row, rows per warp
+    const int lane = threadIdx.x & 31, rw = lane / NL, q = lane - rw * NL;
     const int vrows = a.H - 2 * a.w2;
     const long long nrows = (long long)a.B * vrows;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long r = warp * RW + rw;
     const bool active = rw < RW && r < nrows;
     if (r >= nrows) r = nrows - 1;
-    const int base = min(rw, RW - 1) * nOct;                   // first lane of this row's segment
+    const int base = min(rw, RW - 1) * NL;                     // first lane of this row's segment
     const int f = (int)(r / vrows), y = (int)(r % vrows) + a.w2;
     const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + q * 8;
     const uint16_t* cp = a.col + (rw < RW ? rowBase : 0);
     const size_t outRow = ((size_t)f * a.H + y) * a.W;
     const int bs = 2 * a.w2 + 1;
-    const unsigned kb = (unsigned)q * 8u;
+    const int ostep = NL * 8;                                  // disparities (= u16 elements) between a lane's octets
+    uint16_t* rowsm = sums + (size_t)(threadIdx.x >> 5) * sumsPerWarp + min(rw, RW - 1) * (a.D + 8);
+    uint16_t* mine = rowsm + q * 8;
+    const int sumsAlt = 4 * sumsPerWarp;                   // second copy of the sums area: steps alternate
 
-    uint4 hs = make_uint4(0, 0, 0, 0);
+    int rot[4];                                                // the other lanes of a five-lane row
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rot[k] = min(base + (q + k + 1) % NL, 31);
+    unsigned hs[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) hs[i] = 0;
     for (int j = 0; j < bs; ++j) {
-        const uint4 v = ld128(cp + (size_t)j * a.Dp);
-        hs.x += v.x; hs.y += v.y; hs.z += v.z; hs.w += v.w;
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+            const uint4 v = ld128(cp + (size_t)j * a.Dp + o * ostep);
+            hs[4 * o] += v.x; hs[4 * o + 1] += v.y; hs[4 * o + 2] += v.z; hs[4 * o + 3] += v.w;
+            if (RING) ring[(j * OPL + o) * 128] = v;
+        }
     }
-    // The per-pixel epilogue (texture test, sub-pixel division, store) is identical on the lanes of a row, so it is
-    // deferred: lane q keeps the winner of every nOct-th step and the lanes of a row finish nOct pixels at once.
+    const int xEnd = a.width1 - a.w2;
+    // ring slots (in uint4 units of this lane): column bs + t enters, column t leaves, column bs + BM_PF + t is requested
+    const int slotStride = OPL * 128, ringLen = ringSlots * slotStride;
+    int sIn = (bs % ringSlots) * slotStride, sOut = 0, sReq = ((bs + BM_PF) % ringSlots) * slotStride;
+    if (RING) {
+#pragma unroll
+        for (int k = 0; k < BM_PF; ++k) {
+            if (bs + k < a.width1) {
+#pragma unroll
+                for (int o = 0; o < OPL; ++o)
+                    cp_async16(ring + ((bs + k) % ringSlots) * slotStride + o * 128, cp + (size_t)(bs + k) * a.Dp + o * ostep);
+            }
+            cp_async_commit();
+        }
+    }
     unsigned svKey = 0, svP = 0, svN = 0;
     int svX = -1, sc = 0;
+    // texture of the pixel this lane finishes in the current round, and of the next round's
+    const int* tp = a.tex + outRow + a.lofs;
+    int texCur = tp[min(a.w2 + q, xEnd - 1)], texNext = 0;
     auto flush = [&]() {
-        if (svX >= 0 && active) {
-            const size_t oi = outRow + svX;
-            if (a.tex[oi] >= a.texThr) {
-                const int minsad = (int)(svKey >> 16), mind = (int)(svKey & 0xffffu);
-                const int p = (int)svP, n = (int)svN;
-                const int den = p + n - 2 * minsad + abs(p - n);
-                a.disp[oi] = (int16_t)((((a.D - 1 - mind) * 256) + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
-            }
+        if (svX >= 0 && active && texCur >= a.texThr) {
+            const int minsad = (int)(svKey >> 16), mind = (int)(svKey & 0xffffu);
+            const int p = (int)svP, n = (int)svN;
+            const int den = p + n - 2 * minsad + abs(p - n);
+            a.disp[outRow + svX] = (int16_t)((((a.D - 1 - mind) * 256) + (den != 0 ? (p - n) * 256 / den : 0) + 15) >> 4);
         }
         svX = -1;
     };
-    const int xEnd = a.width1 - a.w2;
+    // running pointers to the columns requested / entering / leaving
+    const uint16_t* pn = cp + (size_t)(RING ? bs + BM_PF : bs) * a.Dp;
+    const uint16_t* po = cp;
+    int colReq = bs + BM_PF, alt = 0;
     for (int xp = a.w2; xp < xEnd; ++xp) {
-        const unsigned Sf[4] = {hs.x, hs.y, hs.z, hs.w};
-        // first argmin through (SAD << 16) | k keys: low halves by a shift-add, high halves by a mask-or, 32-bit min3
-        unsigned key = __vimin3_u32((Sf[0] << 16) + kb, (Sf[0] & 0xffff0000u) | (kb + 1), (Sf[1] << 16) + (kb + 2));
-        key = __vimin3_u32(key, (Sf[1] & 0xffff0000u) | (kb + 3), (Sf[2] << 16) + (kb + 4));
-        key = __vimin3_u32(key, (Sf[2] & 0xffff0000u) | (kb + 5), (Sf[3] << 16) + (kb + 6));
-        key = min(key, (Sf[3] & 0xffff0000u) | (kb + 7));
+        uint4 nx[OPL], od[OPL];
+        if (RING) {
+            if (colReq < a.width1) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned other = __shfl_down_sync(FULL, key, o);
-            if (q + o < nOct) key = min(key, other);
-        }
-        key = __shfl_sync(FULL, key, base);
-        const int minsad = (int)(key >> 16), mind = (int)(key & 0xffffu);
-        bool reject = false;
-        if (a.uniq > 0) {
-            const int thresh = minsad + (minsad * a.uniq / 100);
-            bool bad = false;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = (int)kb + j;
-                const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
-                bad |= (k < mind - 1 || k > mind + 1) && (s <= thresh);
+                for (int o = 0; o < OPL; ++o) cp_async16(ring + sReq + o * 128, pn + o * ostep);
             }
-            const unsigned bal = __ballot_sync(FULL, bad && rw < RW);
-            const unsigned gmask = (nOct == 32) ? FULL : (((1u << nOct) - 1u) << base);
-            reject = (bal & gmask) != 0u;
+            cp_async_commit();
+            ++colReq;
+            sReq += slotStride; if (sReq == ringLen) sReq = 0;
+            cp_async_wait<BM_PF>();                            // column bs + t (requested BM_PF steps ago) has landed
+#pragma unroll
+            for (int o = 0; o < OPL; ++o) { nx[o] = ring[sIn + o * 128]; od[o] = ring[sOut + o * 128]; }
+            sIn += slotStride; if (sIn == ringLen) sIn = 0;
+            sOut += slotStride; if (sOut == ringLen) sOut = 0;
+        } else if (xp + 1 < xEnd) {
+#pragma unroll
+            for (int o = 0; o < OPL; ++o) { nx[o] = ld128(pn + o * ostep); od[o] = ld128(po + o * ostep); }
         }
+        pn += a.Dp; po += a.Dp;
+        if (sc == 0) texNext = tp[min(xp + NL + q, xEnd - 1)];
+#pragma unroll
+        for (int o = 0; o < OPL; ++o)
+            if (rw < RW) st128(mine + alt + o * ostep, make_uint4(hs[4 * o], hs[4 * o + 1], hs[4 * o + 2], hs[4 * o + 3]));
+        // first argmin: keys (SAD << 16) | k
+        unsigned kq[OPL * 2];
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+            const unsigned k0 = (unsigned)(q * 8 + o * ostep);
+            kq[2 * o] = __vimin3_u32((hs[4 * o] << 16) + k0, (hs[4 * o] & 0xffff0000u) | (k0 + 1), (hs[4 * o + 1] << 16) + (k0 + 2));
+            kq[2 * o] = __vimin3_u32(kq[2 * o], (hs[4 * o + 1] & 0xffff0000u) | (k0 + 3), (hs[4 * o + 2] << 16) + (k0 + 4));
+            kq[2 * o + 1] = __vimin3_u32((hs[4 * o + 2] & 0xffff0000u) | (k0 + 5), (hs[4 * o + 3] << 16) + (k0 + 6),
+                                         (hs[4 * o + 3] & 0xffff0000u) | (k0 + 7));
+        }
+        unsigned key = min(kq[0], kq[1]);
+#pragma unroll
+        for (int o = 1; o < OPL; ++o) key = __vimin3_u32(key, kq[2 * o], kq[2 * o + 1]);
+        if (NL == 5) {
+            // all-to-all over the row's five lanes: four independent shuffles instead of a ladder of three plus a broadcast
+            const unsigned k1 = __shfl_sync(FULL, key, rot[0]), k2 = __shfl_sync(FULL, key, rot[1]);
+            const unsigned k3 = __shfl_sync(FULL, key, rot[2]), k4 = __shfl_sync(FULL, key, rot[3]);
+            key = __vimin3_u32(__vimin3_u32(key, k1, k2), k3, k4);
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                if (o < NL) {                                  // warp-uniform
+                    const unsigned other = __shfl_down_sync(FULL, key, o);
+                    if (q + o < NL) key = min(key, other);
+                }
+            }
+            if (NL > 1) key = __shfl_sync(FULL, key, base);
+        }
+        __syncwarp();                                          // the row's sums are in shared memory
+        const int minsad = (int)(key >> 16), mind = (int)(key & 0xffffu);
         const int ip = (mind + 1 < a.D) ? mind + 1 : a.D - 2;
         const int in = (mind > 0) ? mind - 1 : 1;
-        unsigned vp = pick16b(Sf, ip & 7), vn = pick16b(Sf, in & 7);
-        vp = __shfl_sync(FULL, vp, base + (ip >> 3));
-        vn = __shfl_sync(FULL, vn, base + (in >> 3));
+        const unsigned vp = rowsm[alt + ip], vn = rowsm[alt + in];
+        alt ^= sumsAlt;                                        // the next step writes the other copy: one warp barrier per step
+        bool reject = false;
+        if (a.uniq > 0) {
+            // another disparity outside mind-1..mind+1 within the margin: count the lane's sums <= thresh and take off
+            // those of the three exempt positions that lie in this lane's octets (mind itself always counts)
+            const int thresh = minsad + (minsad * a.uniq / 100);
+            const unsigned t2 = (unsigned)min(thresh, 0xffff) * 0x10001u;
+            unsigned cnt2 = 0;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) cnt2 += __vsetleu2(hs[i], t2);
+            const int cnt = (int)((cnt2 & 0xffffu) + (cnt2 >> 16));
+            auto minelane = [&](int k) -> bool { return ((k >> 3) % NL) == q; };
+            int exempt = minelane(mind) ? 1 : 0;
+            if (mind > 0 && minelane(mind - 1) && (int)vn <= thresh) ++exempt;
+            if (mind + 1 < a.D && minelane(mind + 1) && (int)vp <= thresh) ++exempt;
+            const unsigned bal = __ballot_sync(FULL, cnt > exempt && rw < RW);
+            const unsigned gmask = (NL == 32) ? FULL : (((1u << NL) - 1u) << base);
+            reject = (bal & gmask) != 0u;
+        }
         if (sc == q) { svKey = key; svP = vp; svN = vn; svX = reject ? -1 : xp + a.lofs; }
-        if (++sc == nOct) { flush(); sc = 0; }
-        if (xp + 1 < xEnd) {
-            const uint4 nx = ld128(cp + (size_t)(xp + 1 + a.w2) * a.Dp);
-            const uint4 od = ld128(cp + (size_t)(xp - a.w2) * a.Dp);
-            hs.x += nx.x - od.x; hs.y += nx.y - od.y; hs.z += nx.z - od.z; hs.w += nx.w - od.w;
+        if (++sc == NL) { flush(); sc = 0; texCur = texNext; }
+        if (!RING && xp + 1 >= xEnd) {
+#pragma unroll
+            for (int o = 0; o < OPL; ++o) nx[o] = od[o] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+            hs[4 * o] += nx[o].x - od[o].x; hs[4 * o + 1] += nx[o].y - od[o].y;
+            hs[4 * o + 2] += nx[o].z - od[o].z; hs[4 * o + 3] += nx[o].w - od[o].w;
         }
     }
+    if (RING) cp_async_wait<0>();
     flush();
+}
+
+static int bm_sums_per_warp(int D, int opl) { return ((32 / ((D / 8) / opl)) * (D + 8) + 7) / 8 * 8; }
+static size_t bm_wta_smem(int D, int opl, int slots) { return (size_t)2 * 4 * bm_sums_per_warp(D, opl) * 2 + (size_t)slots * opl * 128 * 16; }
+
+template <int OPL, bool RING>
+static void launch_bm_wta(mvsv_ctx* c, const BmArgs& a, int ringSlots)
+{
+    const int NL = (a.D / 8) / OPL, rowsPerWarp = 32 / NL;
+    const long long warps = ((long long)a.B * (a.H - 2 * a.w2) + rowsPerWarp - 1) / rowsPerWarp;
+    static bool configured[64] = {};            // per device: a process may drive several GPUs
+    if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
+        cudaFuncSetAttribute(k_bm_wta<OPL, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (c->device >= 0 && c->device < 64) configured[c->device] = true;
+    }
+    k_bm_wta<OPL, RING><<<(unsigned)((warps * 32 + 127) / 128), 128, bm_wta_smem(a.D, OPL, RING ? ringSlots : 0), c->stream>>>(
+        a, ringSlots, bm_sums_per_warp(a.D, OPL));
 }
 
 __global__ void k_fill16(int16_t* p, size_t n, int16_t v)
@@ -277,7 +392,11 @@ void launch_bm(mvsv_ctx* c, int B)
     a.col = c->bm_col; a.tex = c->bm_tex2; a.disp = c->disp; a.W = W; a.H = H; a.width1 = n.width1; a.D = n.D; a.Dp = n.Dp;
     a.lofs = n.lofs; a.w2 = n.w2; a.texThr = n.tex; a.uniq = n.uniq; a.B = B;
     KernelTimer kt(c, KID_BM_WTA);
-    const int rowsPerWarp = 32 / (n.D / 8);
-    const long long warps = ((long long)B * (H - 2 * n.w2) + rowsPerWarp - 1) / rowsPerWarp;
-    k_bm_wta<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, c->stream>>>(a);
+    // two octets per lane (numDisp is a multiple of 16) with the window ring while two CTAs fit an SM, one octet per
+    // lane while one CTA fits, else (blockSize > ~100) without the ring
+    const int slots = n.bs + 1 + BM_PF;
+    const size_t twoPerSm = 113 * 1024, onePerSm = 226 * 1024;           // 228 KB per SM, 1 KB reserved per CTA
+    if (bm_wta_smem(n.D, 2, slots) <= twoPerSm) launch_bm_wta<2, true>(c, a, slots);
+    else if (bm_wta_smem(n.D, 1, slots) <= onePerSm) launch_bm_wta<1, true>(c, a, slots);
+    else launch_bm_wta<2, false>(c, a, slots);
 }
