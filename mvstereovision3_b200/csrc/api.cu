@@ -180,6 +180,7 @@ int normalise_bm(mvsv_ctx* c, const mvsv_bm_params* p, BmNorm* n)
     while (g * 8 < n->D) g <<= 1;
     n->G = g; n->Dp = n->D; n->w2 = n->bs / 2;      // lanes: next power of two; storage stride: numDisp itself
     n->lofs = n->D - 1; n->width1 = c->W - n->D + 1; n->FILT = -16;
+    n->col8 = n->bs * 2 * n->cap <= 255;
     return MVSV_OK;
 }
 

@@ -8,6 +8,8 @@
 // fused in one row-marching kernel with the same 8-values-per-lane packed u16x2 layout as SGBM.
 #include "mvsv_internal.h"
 
+#include <algorithm>
+
 #include <cstdlib>
 
 namespace {
@@ -104,7 +106,11 @@ __device__ __forceinline__ void bm_acc(unsigned (&acc)[4], const uint2& e, const
 // The absolute differences of the last blockSize rows stay in a per-thread shared-memory ring (8 bytes per row), so
 // the row that leaves the window is not evaluated a second time.
 // Threads are numbered (column, octet) with exactly D / 8 octets per column -- not a power of two as in the row scans, so
-// no lane idles at D = 80 -- and consecutive threads store consecutive 16-byte pieces of the volume.
+// no lane idles at D = 80 -- and consecutive threads store consecutive pieces of the volume.
+// B8 (blockSize * 2 * cap <= 255, e.g. bm.yml: 21 * 4 = 84): a column sum fits a byte, so the volume is stored as one
+// byte per cell and the running sums stay packed four to a register: acc - f + e is exact as plain 32-bit arithmetic
+// because every byte of the result is a window sum in 0..255 (no carry leaves a byte).
+template <bool B8>
 __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ preL, const uint8_t* __restrict__ preR,
                                                    size_t pitch, int H, int width1, int D, int lofs, int w2,
                                                    uint16_t* __restrict__ col)
@@ -124,21 +130,29 @@ __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ p
     const int bs = 2 * w2 + 1;
     uint2* ring = bm_ring + threadIdx.x;
     unsigned acc[4] = {0, 0, 0, 0};
+    uint2 acc8 = make_uint2(0u, 0u);
     for (int y = 0; y < bs; ++y) {
         const uint2 e = bm_ad8(pl + (size_t)y * pitch, pr + (size_t)y * pw, sel);
         ring[y * 128] = e;
-        bm_acc(acc, e, make_uint2(0u, 0u));
+        if (B8) { acc8.x += e.x; acc8.y += e.y; }
+        else bm_acc(acc, e, make_uint2(0u, 0u));
     }
-    uint16_t* out = col + ((size_t)blockIdx.y * H * width1 + xp) * Dp + q * 8;
+    const size_t cell0 = ((size_t)blockIdx.y * H * width1 + xp) * Dp + q * 8, rowCells = (size_t)width1 * Dp;
+    uint16_t* out = col + cell0 + (size_t)w2 * rowCells;
+    uint8_t* out8 = reinterpret_cast<uint8_t*>(col) + cell0 + (size_t)w2 * rowCells;
+    pl += (size_t)bs * pitch; pr += (size_t)bs * pw;         // the row that enters next
     int slot = 0;                                            // ring slot of the oldest row (y - w2)
 #pragma unroll 2
     for (int y = w2; y < H - w2; ++y) {
-        st128(out + (size_t)y * width1 * Dp, make_uint4(acc[0], acc[1], acc[2], acc[3]));
+        if (B8) { *reinterpret_cast<uint2*>(out8) = acc8; out8 += rowCells; }
+        else { st128(out, make_uint4(acc[0], acc[1], acc[2], acc[3])); out += rowCells; }
         if (y + 1 < H - w2) {
-            const uint2 e = bm_ad8(pl + (size_t)(y + 1 + w2) * pitch, pr + (size_t)(y + 1 + w2) * pw, sel);
+            const uint2 e = bm_ad8(pl, pr, sel);
+            pl += pitch; pr += pw;
             const uint2 f = ring[slot * 128];
             ring[slot * 128] = e;
-            bm_acc(acc, e, f);
+            if (B8) { acc8.x += e.x - f.x; acc8.y += e.y - f.y; }
+            else bm_acc(acc, e, f);
             if (++slot == bs) slot = 0;
         }
     }
@@ -150,29 +164,34 @@ struct BmArgs {
 };
 
 // Winner-take-all over the horizontal window sums of `col`.  A row of the volume is scanned left to right by NL
-// adjacent lanes; lane q holds the octets q, q + NL, ... (OPL of them: 8 * OPL disparities in 4 * OPL packed registers)
-// of the running window sum, so the lanes of a row touch contiguous 16-byte pieces.  bm.yml (D = 80) runs with OPL = 2:
-// five lanes per row, six rows per warp.  Per step and lane: the first argmin through (SAD << 16) | k keys (one
-// shift-add or mask-or per value, 32-bit min3), a shfl_down ladder over the row's NL lanes, and the window update from
-// the column that enters and the one that leaves.
+// adjacent lanes, each holding OPL octets (8 * OPL disparities, 4 * OPL packed registers) of the running window sum:
+// with 16-bit column sums lane q holds the octets q, q + NL, ..., so that the lanes of a row touch contiguous 16-byte
+// pieces; with byte column sums (B8, OPL = 2) lane q holds the sixteen disparities 16q..16q+15, one 16-byte piece.
+// bm.yml (D = 80): five lanes per row, six rows per warp.  Per step and lane: the first argmin through
+// (SAD << 16) | k keys (one shift-add or mask-or per value, 32-bit min3), a key exchange over the row's NL lanes, and
+// the window update from the column that enters and the one that leaves.
 //   RING: every column of the volume is read from HBM once.  A lane copies its pieces of column x + w2 + 1 + PF with
 //   cp.async into a private shared-memory ring of blockSize + 1 + PF slots and reads both the entering and the leaving
 //   column from there (without the ring the leaving column is a second HBM read 2 * w2 + 1 steps later: the rows in
 //   flight hold 230 MB of window at bm.yml, twice the L2 -- ncu: 14.5 GB of DRAM reads for a 7.1 GB volume).
 // The winner's neighbours S[mind -/+ 1] are read from a shared-memory copy of the row's sums (any lane of the row can
-// address any disparity there, no register indexing).  The per-pixel epilogue (texture test, sub-pixel division,
-// store) is identical on the lanes of a row, so it is deferred: lane q keeps the winner of every NL-th step and the
-// lanes of a row finish NL pixels at once; the texture value of a lane's pixel is requested one round ahead.
+// address any disparity there, no register indexing; two copies used in turn: one warp barrier per step).  The
+// per-pixel epilogue (texture test, sub-pixel division, store) is identical on the lanes of a row, so it is deferred:
+// lane q keeps the winner of every NL-th step and the lanes of a row finish NL pixels at once; the texture value of a
+// lane's pixel is requested one round ahead.
 constexpr int BM_PF = 3;       // columns in flight ahead of the window (RING)
 
-template <int OPL, bool RING>
-__global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sumsPerWarp)
+template <int OPL, bool RING, bool B8>
+__global__ void __launch_bounds__(256) k_bm_wta(BmArgs a, int ringSlots, int sumsPerWarp)
 {
+    static_assert(!B8 || OPL == 2, "byte volume: sixteen disparities per lane");
     constexpr int NR = 4 * OPL;                                // packed registers per lane
+    constexpr int PC = B8 ? 1 : OPL;                           // 16-byte pieces per lane and column
     extern __shared__ __align__(16) unsigned char bm_smem[];
-    // layout: sums[2 copies][4 warps][sumsPerWarp = RW rows x (D + 8), rounded up to 8] u16 | ring[slots][OPL][128 lanes] uint4
+    // layout: sums[2 copies][warps][sumsPerWarp = RW rows x (D + 8), rounded up to 8] u16 | ring[slots][PC][threads] uint4
+    const int nthr = blockDim.x, nwarps = nthr >> 5;
     uint16_t* sums = reinterpret_cast<uint16_t*>(bm_smem);
-    uint4* ring = reinterpret_cast<uint4*>(bm_smem + (size_t)2 * 4 * sumsPerWarp * sizeof(uint16_t)) + threadIdx.x;
+    uint4* ring = reinterpret_cast<uint4*>(bm_smem + (size_t)2 * nwarps * sumsPerWarp * sizeof(uint16_t)) + threadIdx.x;
     const int nOct = a.D >> 3, NL = nOct / OPL, RW = 32 / NL;  // lanes per row, rows per warp
     const int lane = threadIdx.x & 31, rw = lane / NL, q = lane - rw * NL;
     const int vrows = a.H - 2 * a.w2;
@@ -183,14 +202,42 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sum
     if (r >= nrows) r = nrows - 1;
     const int base = min(rw, RW - 1) * NL;                     // first lane of this row's segment
     const int f = (int)(r / vrows), y = (int)(r % vrows) + a.w2;
-    const size_t rowBase = ((size_t)f * a.H + y) * a.width1 * a.Dp + q * 8;
-    const uint16_t* cp = a.col + (rw < RW ? rowBase : 0);
+    // byte offsets into the volume: this lane's first piece of column 0, the next piece, the next column
+    const int esz = B8 ? 1 : 2;
+    const size_t rowBase = (((size_t)f * a.H + y) * a.width1 * a.Dp + q * (B8 ? 16 : 8)) * esz;
+    const unsigned char* cp = reinterpret_cast<const unsigned char*>(a.col) + (rw < RW ? rowBase : 0);
+    const int pstep = NL * 16;                                 // bytes between a lane's pieces (16-bit volume)
+    const size_t cstep = (size_t)a.Dp * esz;                   // bytes between columns
+    const int k00 = B8 ? q * 16 : q * 8, kstep = B8 ? 8 : NL * 8;      // first disparity of octet o: k00 + o * kstep
     const size_t outRow = ((size_t)f * a.H + y) * a.W;
     const int bs = 2 * a.w2 + 1;
-    const int ostep = NL * 8;                                  // disparities (= u16 elements) between a lane's octets
     uint16_t* rowsm = sums + (size_t)(threadIdx.x >> 5) * sumsPerWarp + min(rw, RW - 1) * (a.D + 8);
-    uint16_t* mine = rowsm + q * 8;
-    const int sumsAlt = 4 * sumsPerWarp;                   // second copy of the sums area: steps alternate
+    uint16_t* mine = rowsm + k00;
+    const int sumsAlt = nwarps * sumsPerWarp;                  // second copy of the sums area: steps alternate
+
+    // w (a column's pieces) added to / taken off the packed sums
+    auto addcol = [&](unsigned (&hs)[NR], const uint4 (&w)[PC]) {
+        if (B8) {
+            hs[0] += __byte_perm(w[0].x, 0, 0x4140); hs[1] += __byte_perm(w[0].x, 0, 0x4342);
+            hs[2] += __byte_perm(w[0].y, 0, 0x4140); hs[3] += __byte_perm(w[0].y, 0, 0x4342);
+            hs[4] += __byte_perm(w[0].z, 0, 0x4140); hs[5] += __byte_perm(w[0].z, 0, 0x4342);
+            hs[6] += __byte_perm(w[0].w, 0, 0x4140); hs[7] += __byte_perm(w[0].w, 0, 0x4342);
+        } else {
+#pragma unroll
+            for (int o = 0; o < PC; ++o) { hs[4 * o] += w[o].x; hs[4 * o + 1] += w[o].y; hs[4 * o + 2] += w[o].z; hs[4 * o + 3] += w[o].w; }
+        }
+    };
+    auto subcol = [&](unsigned (&hs)[NR], const uint4 (&w)[PC]) {
+        if (B8) {
+            hs[0] -= __byte_perm(w[0].x, 0, 0x4140); hs[1] -= __byte_perm(w[0].x, 0, 0x4342);
+            hs[2] -= __byte_perm(w[0].y, 0, 0x4140); hs[3] -= __byte_perm(w[0].y, 0, 0x4342);
+            hs[4] -= __byte_perm(w[0].z, 0, 0x4140); hs[5] -= __byte_perm(w[0].z, 0, 0x4342);
+            hs[6] -= __byte_perm(w[0].w, 0, 0x4140); hs[7] -= __byte_perm(w[0].w, 0, 0x4342);
+        } else {
+#pragma unroll
+            for (int o = 0; o < PC; ++o) { hs[4 * o] -= w[o].x; hs[4 * o + 1] -= w[o].y; hs[4 * o + 2] -= w[o].z; hs[4 * o + 3] -= w[o].w; }
+        }
+    };
 
     int rot[4];                                                // the other lanes of a five-lane row
 #pragma unroll
@@ -199,24 +246,25 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sum
 #pragma unroll
     for (int i = 0; i < NR; ++i) hs[i] = 0;
     for (int j = 0; j < bs; ++j) {
+        uint4 w[PC];
 #pragma unroll
-        for (int o = 0; o < OPL; ++o) {
-            const uint4 v = ld128(cp + (size_t)j * a.Dp + o * ostep);
-            hs[4 * o] += v.x; hs[4 * o + 1] += v.y; hs[4 * o + 2] += v.z; hs[4 * o + 3] += v.w;
-            if (RING) ring[(j * OPL + o) * 128] = v;
+        for (int o = 0; o < PC; ++o) {
+            w[o] = ld128(cp + (size_t)j * cstep + o * pstep);
+            if (RING) ring[(j * PC + o) * nthr] = w[o];
         }
+        addcol(hs, w);
     }
     const int xEnd = a.width1 - a.w2;
     // ring slots (in uint4 units of this lane): column bs + t enters, column t leaves, column bs + BM_PF + t is requested
-    const int slotStride = OPL * 128, ringLen = ringSlots * slotStride;
+    const int slotStride = PC * nthr, ringLen = ringSlots * slotStride;
     int sIn = (bs % ringSlots) * slotStride, sOut = 0, sReq = ((bs + BM_PF) % ringSlots) * slotStride;
     if (RING) {
 #pragma unroll
         for (int k = 0; k < BM_PF; ++k) {
             if (bs + k < a.width1) {
 #pragma unroll
-                for (int o = 0; o < OPL; ++o)
-                    cp_async16(ring + ((bs + k) % ringSlots) * slotStride + o * 128, cp + (size_t)(bs + k) * a.Dp + o * ostep);
+                for (int o = 0; o < PC; ++o)
+                    cp_async16(ring + ((bs + k) % ringSlots) * slotStride + o * nthr, cp + (size_t)(bs + k) * cstep + o * pstep);
             }
             cp_async_commit();
         }
@@ -236,38 +284,41 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sum
         svX = -1;
     };
     // running pointers to the columns requested / entering / leaving
-    const uint16_t* pn = cp + (size_t)(RING ? bs + BM_PF : bs) * a.Dp;
-    const uint16_t* po = cp;
+    const unsigned char* pn = cp + (size_t)(RING ? bs + BM_PF : bs) * cstep;
+    const unsigned char* po = cp;
     int colReq = bs + BM_PF, alt = 0;
     for (int xp = a.w2; xp < xEnd; ++xp) {
-        uint4 nx[OPL], od[OPL];
+        uint4 nx[PC], od[PC];
         if (RING) {
             if (colReq < a.width1) {
 #pragma unroll
-                for (int o = 0; o < OPL; ++o) cp_async16(ring + sReq + o * 128, pn + o * ostep);
+                for (int o = 0; o < PC; ++o) cp_async16(ring + sReq + o * nthr, pn + o * pstep);
             }
             cp_async_commit();
             ++colReq;
             sReq += slotStride; if (sReq == ringLen) sReq = 0;
             cp_async_wait<BM_PF>();                            // column bs + t (requested BM_PF steps ago) has landed
 #pragma unroll
-            for (int o = 0; o < OPL; ++o) { nx[o] = ring[sIn + o * 128]; od[o] = ring[sOut + o * 128]; }
+            for (int o = 0; o < PC; ++o) { nx[o] = ring[sIn + o * nthr]; od[o] = ring[sOut + o * nthr]; }
             sIn += slotStride; if (sIn == ringLen) sIn = 0;
             sOut += slotStride; if (sOut == ringLen) sOut = 0;
         } else if (xp + 1 < xEnd) {
 #pragma unroll
-            for (int o = 0; o < OPL; ++o) { nx[o] = ld128(pn + o * ostep); od[o] = ld128(po + o * ostep); }
+            for (int o = 0; o < PC; ++o) { nx[o] = ld128(pn + o * pstep); od[o] = ld128(po + o * pstep); }
+        } else {
+#pragma unroll
+            for (int o = 0; o < PC; ++o) nx[o] = od[o] = make_uint4(0, 0, 0, 0);
         }
-        pn += a.Dp; po += a.Dp;
+        pn += cstep; po += cstep;
         if (sc == 0) texNext = tp[min(xp + NL + q, xEnd - 1)];
 #pragma unroll
         for (int o = 0; o < OPL; ++o)
-            if (rw < RW) st128(mine + alt + o * ostep, make_uint4(hs[4 * o], hs[4 * o + 1], hs[4 * o + 2], hs[4 * o + 3]));
+            if (rw < RW) st128(mine + alt + o * kstep, make_uint4(hs[4 * o], hs[4 * o + 1], hs[4 * o + 2], hs[4 * o + 3]));
         // first argmin: keys (SAD << 16) | k
         unsigned kq[OPL * 2];
 #pragma unroll
         for (int o = 0; o < OPL; ++o) {
-            const unsigned k0 = (unsigned)(q * 8 + o * ostep);
+            const unsigned k0 = (unsigned)(k00 + o * kstep);
             kq[2 * o] = __vimin3_u32((hs[4 * o] << 16) + k0, (hs[4 * o] & 0xffff0000u) | (k0 + 1), (hs[4 * o + 1] << 16) + (k0 + 2));
             kq[2 * o] = __vimin3_u32(kq[2 * o], (hs[4 * o + 1] & 0xffff0000u) | (k0 + 3), (hs[4 * o + 2] << 16) + (k0 + 4));
             kq[2 * o + 1] = __vimin3_u32((hs[4 * o + 2] & 0xffff0000u) | (k0 + 5), (hs[4 * o + 3] << 16) + (k0 + 6),
@@ -307,7 +358,7 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sum
 #pragma unroll
             for (int i = 0; i < NR; ++i) cnt2 += __vsetleu2(hs[i], t2);
             const int cnt = (int)((cnt2 & 0xffffu) + (cnt2 >> 16));
-            auto minelane = [&](int k) -> bool { return ((k >> 3) % NL) == q; };
+            auto minelane = [&](int k) -> bool { return (B8 ? (k >> 4) : ((k >> 3) % NL)) == q; };
             int exempt = minelane(mind) ? 1 : 0;
             if (mind > 0 && minelane(mind - 1) && (int)vn <= thresh) ++exempt;
             if (mind + 1 < a.D && minelane(mind + 1) && (int)vp <= thresh) ++exempt;
@@ -317,34 +368,43 @@ __global__ void __launch_bounds__(128) k_bm_wta(BmArgs a, int ringSlots, int sum
         }
         if (sc == q) { svKey = key; svP = vp; svN = vn; svX = reject ? -1 : xp + a.lofs; }
         if (++sc == NL) { flush(); sc = 0; texCur = texNext; }
-        if (!RING && xp + 1 >= xEnd) {
-#pragma unroll
-            for (int o = 0; o < OPL; ++o) nx[o] = od[o] = make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int o = 0; o < OPL; ++o) {
-            hs[4 * o] += nx[o].x - od[o].x; hs[4 * o + 1] += nx[o].y - od[o].y;
-            hs[4 * o + 2] += nx[o].z - od[o].z; hs[4 * o + 3] += nx[o].w - od[o].w;
-        }
+        addcol(hs, nx);
+        subcol(hs, od);
     }
     if (RING) cp_async_wait<0>();
     flush();
 }
 
 static int bm_sums_per_warp(int D, int opl) { return ((32 / ((D / 8) / opl)) * (D + 8) + 7) / 8 * 8; }
-static size_t bm_wta_smem(int D, int opl, int slots) { return (size_t)2 * 4 * bm_sums_per_warp(D, opl) * 2 + (size_t)slots * opl * 128 * 16; }
+// shared memory of one warp: two copies of its rows' sums + its lanes' ring
+static size_t bm_wta_warp_smem(int D, int opl, int pieces, int slots) { return (size_t)2 * bm_sums_per_warp(D, opl) * 2 + (size_t)slots * pieces * 32 * 16; }
+// warps per CTA (2..8) that put the most warps on an SM (228 KB, 1 KB reserved per CTA); 0 = not even two warps fit
+static int bm_wta_cta_warps(size_t warpBytes, int* warpsPerSm)
+{
+    int best = 0, bestTotal = 0;
+    const int order[] = {4, 5, 6, 3, 7, 8, 2};
+    for (int nw : order) {
+        const size_t cta = nw * warpBytes + 1024;
+        if (nw * warpBytes > 226 * 1024) continue;
+        const int total = std::min(64, (int)(228 * 1024 / cta) * nw);
+        if (total > bestTotal) { bestTotal = total; best = nw; }
+    }
+    *warpsPerSm = bestTotal;
+    return best;
+}
 
-template <int OPL, bool RING>
-static void launch_bm_wta(mvsv_ctx* c, const BmArgs& a, int ringSlots)
+template <int OPL, bool RING, bool B8>
+static void launch_bm_wta(mvsv_ctx* c, const BmArgs& a, int ringSlots, int ctaWarps)
 {
     const int NL = (a.D / 8) / OPL, rowsPerWarp = 32 / NL;
     const long long warps = ((long long)a.B * (a.H - 2 * a.w2) + rowsPerWarp - 1) / rowsPerWarp;
     static bool configured[64] = {};            // per device: a process may drive several GPUs
     if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
-        cudaFuncSetAttribute(k_bm_wta<OPL, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        cudaFuncSetAttribute(k_bm_wta<OPL, RING, B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (c->device >= 0 && c->device < 64) configured[c->device] = true;
     }
-    k_bm_wta<OPL, RING><<<(unsigned)((warps * 32 + 127) / 128), 128, bm_wta_smem(a.D, OPL, RING ? ringSlots : 0), c->stream>>>(
+    const size_t smem = ctaWarps * bm_wta_warp_smem(a.D, OPL, B8 ? 1 : OPL, RING ? ringSlots : 0);
+    k_bm_wta<OPL, RING, B8><<<(unsigned)((warps + ctaWarps - 1) / ctaWarps), ctaWarps * 32, smem, c->stream>>>(
         a, ringSlots, bm_sums_per_warp(a.D, OPL));
 }
 
@@ -359,6 +419,7 @@ __global__ void k_fill16(int16_t* p, size_t n, int16_t v)
 void launch_bm(mvsv_ctx* c, int B)
 {
     const BmNorm& n = c->bm;
+    const bool col8 = n.col8 && !(c->debug_flags & 2u);         // debug bit 1: never keep a volume as bytes
     const int W = c->W, H = c->H;
     const size_t npx = (size_t)B * W * H;
     { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
@@ -382,21 +443,31 @@ void launch_bm(mvsv_ctx* c, int B)
         const size_t ringBytes = (size_t)n.bs * 128 * sizeof(uint2);
         static bool configured[64] = {};        // per device: a process may drive several GPUs
         if (c->device < 0 || c->device >= 64 || !configured[c->device]) {
-            cudaFuncSetAttribute(k_bm_colsum, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_bm_colsum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (c->device >= 0 && c->device < 64) configured[c->device] = true;
         }
         KernelTimer kt(c, KID_BM_COLSUM);
-        k_bm_colsum<<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col);
+        if (col8) k_bm_colsum<true><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col);
+        else k_bm_colsum<false><<<grd, 128, ringBytes, c->stream>>>(c->bm_pre[0], c->bm_pre[1], c->pitch, H, n.width1, n.D, n.lofs, n.w2, c->bm_col);
     }
     BmArgs a;
     a.col = c->bm_col; a.tex = c->bm_tex2; a.disp = c->disp; a.W = W; a.H = H; a.width1 = n.width1; a.D = n.D; a.Dp = n.Dp;
     a.lofs = n.lofs; a.w2 = n.w2; a.texThr = n.tex; a.uniq = n.uniq; a.B = B;
     KernelTimer kt(c, KID_BM_WTA);
-    // two octets per lane (numDisp is a multiple of 16) with the window ring while two CTAs fit an SM, one octet per
-    // lane while one CTA fits, else (blockSize > ~100) without the ring
+    // Two octets per lane (numDisp is a multiple of 16) with the window ring while at least eight warps fit an SM
+    // (four with the byte volume's smaller ring), one octet per lane while four do, else (blockSize > ~100) no ring.
     const int slots = n.bs + 1 + BM_PF;
-    const size_t twoPerSm = 113 * 1024, onePerSm = 226 * 1024;           // 228 KB per SM, 1 KB reserved per CTA
-    if (bm_wta_smem(n.D, 2, slots) <= twoPerSm) launch_bm_wta<2, true>(c, a, slots);
-    else if (bm_wta_smem(n.D, 1, slots) <= onePerSm) launch_bm_wta<1, true>(c, a, slots);
-    else launch_bm_wta<2, false>(c, a, slots);
+    int wps = 0, nw;
+    if (col8) {
+        nw = bm_wta_cta_warps(bm_wta_warp_smem(n.D, 2, 1, slots), &wps);
+        if (wps >= 4) launch_bm_wta<2, true, true>(c, a, slots, nw);
+        else launch_bm_wta<2, false, true>(c, a, slots, 4);
+    } else {
+        nw = bm_wta_cta_warps(bm_wta_warp_smem(n.D, 2, 2, slots), &wps);
+        if (wps >= 8) { launch_bm_wta<2, true, false>(c, a, slots, nw); return; }
+        nw = bm_wta_cta_warps(bm_wta_warp_smem(n.D, 1, 1, slots), &wps);
+        if (wps >= 4) launch_bm_wta<1, true, false>(c, a, slots, nw);
+        else launch_bm_wta<2, false, false>(c, a, slots, 4);
+    }
 }

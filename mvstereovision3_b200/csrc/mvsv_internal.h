@@ -24,6 +24,7 @@ struct SgbmNorm {
 struct BmNorm {
     int D, Dp, G, bs, w2, cap, tex, uniq;
     int lofs, width1, FILT;
+    int col8;                   // column sums fit a byte (blockSize * 2 * cap <= 255): the volume is one byte per cell
 };
 
 // kernel ids for the optional per-launch CUDA-event timing (mvsv_profile_*)

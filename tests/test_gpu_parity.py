@@ -78,11 +78,17 @@ def test_fused_sweep_cluster_sizes(oracle, ci, nc):
     check("disp flipped", out[1], oracle.sgbm(l[::-1].copy(), r[::-1].copy(), p))
 
 
+@pytest.mark.parametrize("wide", [0, 2], ids=["auto", "u16"])
 @pytest.mark.parametrize("case", cases.BM_CASES, ids=[c[0] for c in cases.BM_CASES])
-def test_bm_vs_oracle(oracle, golden, case):
+def test_bm_vs_oracle(oracle, golden, case, wide):
+    """Prefilter and disparity against the oracle and the cv2 golden vectors.  "auto": the column-sum volume is one byte
+    per cell where blockSize * 2 * cap <= 255 (bm.yml); "u16": debug flag bit 1 keeps it 16 bits wide."""
     name, p, H, W = case
+    if wide and p["blockSize"] * 2 * p["preFilterCap"] > 255:
+        pytest.skip("the volume is 16 bits wide anyway")
     with api.Engine(W, H, max_batch=2) as e:
         e.set_bm_params(**p)
+        e.debug_set_flags(wide)
         pair = [cases.bm_inputs(name, p, H, W, k) for k in ("ramp", "noise")]
         e.compute(np.stack([pair[0][0], pair[1][0]]), np.stack([pair[0][1], pair[1][1]]), api.STAGE_BM)
         out = e.download(2)["disp"]
