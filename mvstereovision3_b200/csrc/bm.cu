@@ -90,11 +90,20 @@ k_bm_tex_row(const uint16_t* __restrict__ tc, int W, int H, int w2, int* __restr
 // rows with a sliding sum.  The eight right-image bytes start at an arbitrary byte address, so they are cut out of
 // three aligned words with PRMT (the selector is constant per thread); |L - R| is VABSDIFF4 on four bytes at once,
 // widened to packed u16x2 for the running sums; one 128-bit store per row.
+struct BmRaw { unsigned l, w0, w1, w2; };       // a row's operands as loaded: the left byte and three aligned right words
+__device__ __forceinline__ BmRaw bm_load8(const uint8_t* __restrict__ rowL, const unsigned* __restrict__ rowR)
+{
+    BmRaw r; r.l = rowL[0]; r.w0 = rowR[0]; r.w1 = rowR[1]; r.w2 = rowR[2];
+    return r;
+}
+__device__ __forceinline__ uint2 bm_ad8(const BmRaw& r, unsigned sel)
+{
+    const unsigned lb = r.l * 0x01010101u;
+    return make_uint2(__vabsdiffu4(lb, __byte_perm(r.w0, r.w1, sel)), __vabsdiffu4(lb, __byte_perm(r.w1, r.w2, sel)));
+}
 __device__ __forceinline__ uint2 bm_ad8(const uint8_t* __restrict__ rowL, const unsigned* __restrict__ rowR, unsigned sel)
 {
-    const unsigned lb = (unsigned)rowL[0] * 0x01010101u;
-    const unsigned w0 = rowR[0], w1 = rowR[1], w2 = rowR[2];
-    return make_uint2(__vabsdiffu4(lb, __byte_perm(w0, w1, sel)), __vabsdiffu4(lb, __byte_perm(w1, w2, sel)));
+    return bm_ad8(bm_load8(rowL, rowR), sel);
 }
 // acc (packed u16x2) += the eight bytes of e, -= the eight bytes of f
 __device__ __forceinline__ void bm_acc(unsigned (&acc)[4], const uint2& e, const uint2& f)
@@ -140,21 +149,35 @@ __global__ void __launch_bounds__(128) k_bm_colsum(const uint8_t* __restrict__ p
     const size_t cell0 = ((size_t)blockIdx.y * H * width1 + xp) * Dp + q * 8, rowCells = (size_t)width1 * Dp;
     uint16_t* out = col + cell0 + (size_t)w2 * rowCells;
     uint8_t* out8 = reinterpret_cast<uint8_t*>(col) + cell0 + (size_t)w2 * rowCells;
-    pl += (size_t)bs * pitch; pr += (size_t)bs * pw;         // the row that enters next
+    // The operands of the entering rows are requested two rows ahead (each row's loads would otherwise be waited for
+    // on the spot: ncu showed 24 of 25 stall cycles on the long scoreboard); rows past the image repeat the last one.
+    pl += (size_t)(bs - 1) * pitch; pr += (size_t)(bs - 1) * pw;
+    const int lastIn = H - 1;                                // last row that ever enters
+    int yin = bs - 1;
+    if (yin < lastIn) { pl += pitch; pr += pw; ++yin; }
+    BmRaw r0 = bm_load8(pl, pr);
+    if (yin < lastIn) { pl += pitch; pr += pw; ++yin; }
+    BmRaw r1 = bm_load8(pl, pr);
     int slot = 0;                                            // ring slot of the oldest row (y - w2)
-#pragma unroll 2
-    for (int y = w2; y < H - w2; ++y) {
+    // one output row; `cur` holds the operands of the row that enters and is refilled for the row two further down
+    // (two named register sets used in turn: a rotation through moves would wait for the loads it has just issued)
+    auto row = [&](int y, BmRaw& cur) {
         if (B8) { *reinterpret_cast<uint2*>(out8) = acc8; out8 += rowCells; }
         else { st128(out, make_uint4(acc[0], acc[1], acc[2], acc[3])); out += rowCells; }
         if (y + 1 < H - w2) {
-            const uint2 e = bm_ad8(pl, pr, sel);
-            pl += pitch; pr += pw;
+            const uint2 e = bm_ad8(cur, sel);
+            if (yin < lastIn) { pl += pitch; pr += pw; ++yin; }
+            cur = bm_load8(pl, pr);
             const uint2 f = ring[slot * 128];
             ring[slot * 128] = e;
             if (B8) { acc8.x += e.x - f.x; acc8.y += e.y - f.y; }
             else bm_acc(acc, e, f);
             if (++slot == bs) slot = 0;
         }
+    };
+    for (int y = w2; y < H - w2; y += 2) {
+        row(y, r0);
+        if (y + 1 < H - w2) row(y + 1, r1);
     }
 }
 
@@ -408,10 +431,13 @@ static void launch_bm_wta(mvsv_ctx* c, const BmArgs& a, int ringSlots, int ctaWa
         a, ringSlots, bm_sums_per_warp(a.D, OPL));
 }
 
+// n is a multiple of 8 pixels (the image buffers are padded to 16 bytes): one 128-bit store per thread
 __global__ void k_fill16(int16_t* p, size_t n, int16_t v)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const unsigned vv = (unsigned)(uint16_t)v * 0x10001u;
+    if (i + 8 <= n) st128(p + i, make_uint4(vv, vv, vv, vv));
+    else for (size_t k = i; k < n; ++k) p[k] = v;
 }
 
 }  // namespace
@@ -422,7 +448,7 @@ void launch_bm(mvsv_ctx* c, int B)
     const bool col8 = n.col8 && !(c->debug_flags & 2u);         // debug bit 1: never keep a volume as bytes
     const int W = c->W, H = c->H;
     const size_t npx = (size_t)B * W * H;
-    { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx + 255) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
+    { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx / 8 + 256) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
     {
         dim3 blk(128), grd((W + 127) / 128, (H + BM_ROWS - 1) / BM_ROWS, 2 * B);
         KernelTimer kt(c, KID_BM_PREFILTER);
