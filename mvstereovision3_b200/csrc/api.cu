@@ -60,7 +60,7 @@ void free_images(mvsv_ctx* c)
     c->lastB = 0;
     dfree(c->recL);
     dfree(c->d2); dfree(c->disp_raw); dfree(c->disp_med); dfree(c->labels); dfree(c->sizes);
-    dfree(c->bm_tex); dfree(c->bm_tex2); dfree(c->minmax); dfree(c->tm_out);
+    dfree(c->bm_tex2); dfree(c->minmax); dfree(c->tm_out);
 }
 void free_sgbm_volumes(mvsv_ctx* c)
 {
@@ -90,7 +90,6 @@ int alloc_images(mvsv_ctx* c)
     MVSV_CK(c, cudaMalloc(&c->disp_med, npx * sizeof(int16_t)));
     MVSV_CK(c, cudaMalloc(&c->labels, npx * sizeof(int)));
     MVSV_CK(c, cudaMalloc(&c->sizes, npx * sizeof(int)));
-    MVSV_CK(c, cudaMalloc(&c->bm_tex, npx * sizeof(uint16_t)));
     MVSV_CK(c, cudaMalloc(&c->bm_tex2, npx * sizeof(int)));
     select_slot(c, 0);
     return MVSV_OK;

@@ -53,36 +53,48 @@ k_bm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img
     }
 }
 
-// texture: separable window sum of |L - cap|; the column pass slides down BM_ROWS rows per thread
-__global__ void __launch_bounds__(128)
-k_bm_tex_col(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap, uint16_t* __restrict__ tc)
+// texture: window sum of |L - cap| over blockSize x blockSize pixels.  One CTA = 256 adjacent columns (256 - 2*w2 of them
+// produce output) x BM_TEX_ROWS rows: a thread slides the vertical sum of its column down the band; per row the CTA
+// turns the 256 column sums into inclusive prefix sums (shuffle scan per warp + the warps' totals) and an output pixel
+// is the difference of two of them.
+constexpr int BM_TEX_ROWS = 64;
+__global__ void __launch_bounds__(256)
+k_bm_tex(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap, int* __restrict__ tex)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int ya = blockIdx.y * BM_ROWS + w2, yb = min(ya + BM_ROWS, H - w2);
-    if (x >= W || ya >= yb) return;
-    const uint8_t* p = preL + (size_t)blockIdx.z * H * pitch + x;
+    __shared__ int pre[2][256];
+    __shared__ int wtot[2][8];
+    const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+    const int nx = 256 - 2 * w2;
+    const int x0 = w2 + blockIdx.x * nx;                      // first output column of this CTA
+    const int xc = min(x0 - w2 + t, W - 1);                   // this thread's column (clamped: the excess feeds no output)
+    const int ya = w2 + blockIdx.y * BM_TEX_ROWS, yb = min(ya + BM_TEX_ROWS, H - w2);
+    const uint8_t* p = preL + (size_t)blockIdx.z * H * pitch + xc;
     int s = 0;
     for (int dy = -w2; dy <= w2; ++dy) s += abs((int)p[(size_t)(ya + dy) * pitch] - cap);
-    uint16_t* o = tc + (size_t)blockIdx.z * H * W + x;
+    const bool outp = t < nx && x0 + t < W - w2;
+    int* o = tex + ((size_t)blockIdx.z * H + ya) * W + x0 + t;
+    const uint8_t* pin = p + (size_t)(ya + w2 + 1) * pitch;   // row entering / leaving the window of the next output row
+    const uint8_t* pout = p + (size_t)(ya - w2) * pitch;
+    int e = 0, f = 0;
     for (int y = ya; y < yb; ++y) {
-        o[(size_t)y * W] = (uint16_t)s;
-        if (y + 1 < yb) s += abs((int)p[(size_t)(y + 1 + w2) * pitch] - cap) - abs((int)p[(size_t)(y - w2) * pitch] - cap);
-    }
-}
-// row pass: a warp slides along a row segment; lanes own BM_SEG consecutive columns each
-constexpr int BM_SEG = 8;
-__global__ void __launch_bounds__(128)
-k_bm_tex_row(const uint16_t* __restrict__ tc, int W, int H, int w2, int* __restrict__ tex)
-{
-    const int xa = (blockIdx.x * blockDim.x + threadIdx.x) * BM_SEG + w2, y = blockIdx.y + w2;
-    if (xa >= W - w2 || y >= H - w2) return;
-    const size_t base = ((size_t)blockIdx.z * H + y) * W;
-    const int xb = min(xa + BM_SEG, W - w2);
-    int s = 0;
-    for (int dx = -w2; dx <= w2; ++dx) s += tc[base + xa + dx];
-    for (int x = xa; x < xb; ++x) {
-        tex[base + x] = s;
-        if (x + 1 < xb) s += (int)tc[base + x + 1 + w2] - (int)tc[base + x - w2];
+        const int b = (y - ya) & 1;
+        if (y + 1 < yb) { e = *pin; f = *pout; pin += pitch; pout += pitch; }    // requested before the scan
+        int v = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(FULL, v, d);
+            if (lane >= d) v += u;
+        }
+        if (lane == 31) wtot[b][wp] = v;
+        __syncthreads();
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) off += (k < wp) ? wtot[b][k] : 0;
+        pre[b][t] = v + off;
+        __syncthreads();
+        if (outp) *o = pre[b][t + 2 * w2] - (t > 0 ? pre[b][t - 1] : 0);
+        o += W;
+        s += abs(e - cap) - abs(f - cap);
     }
 }
 
@@ -457,10 +469,10 @@ void launch_bm(mvsv_ctx* c, int B)
     const bool any = !(n.lofs >= W || n.width1 < 1) && (H - 2 * n.w2 > 0) && (n.width1 - 2 * n.w2 > 0);
     if (!any) return;
     {
-        dim3 blk(128), grd((W + 127) / 128, (H - 2 * n.w2 + BM_ROWS - 1) / BM_ROWS, B);
-        { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_col<<<grd, blk, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex); }
-        dim3 grd2((W - 2 * n.w2 + 128 * BM_SEG - 1) / (128 * BM_SEG), H - 2 * n.w2, B);
-        { KernelTimer kt(c, KID_BM_TEX); k_bm_tex_row<<<grd2, blk, 0, c->stream>>>(c->bm_tex, W, H, n.w2, c->bm_tex2); }
+        const int nx = 256 - 2 * n.w2;                      // blockSize <= 255: at least two output columns per CTA
+        dim3 grd((W - 2 * n.w2 + nx - 1) / nx, (H - 2 * n.w2 + BM_TEX_ROWS - 1) / BM_TEX_ROWS, B);
+        KernelTimer kt(c, KID_BM_TEX);
+        k_bm_tex<<<grd, 256, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex2);
     }
     {
         const long long threads = (long long)n.width1 * (n.D / 8);

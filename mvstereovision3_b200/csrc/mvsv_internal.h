@@ -115,8 +115,7 @@ struct mvsv_ctx {
     int* sizes = nullptr;                     // [B][H][W]
 
     uint8_t* bm_pre[2] = {nullptr, nullptr};  // [B][H][pitch]
-    uint16_t* bm_tex = nullptr;               // [B][H][W] column sums, then window sums (int32 below)
-    int* bm_tex2 = nullptr;
+    int* bm_tex2 = nullptr;                   // [B][H][W] texture: window sums of |L - cap|
     size_t bm_vol_elems = 0;
     uint16_t* bm_col = nullptr;               // [B][H][width1][Dp]
 
