@@ -503,13 +503,6 @@ __global__ void __launch_bounds__(128) k_sgbm_vdir(AggArgs a, int dxs, int botto
 
 // K3c + K4: right-to-left path r=(+1,0) fused with winner-take-all, uniqueness, sub-pixel interpolation,
 // the disp2 scatter (sequential in x per row, exactly the reference order) and the left-right check.
-__device__ __forceinline__ unsigned pick16(const unsigned (&R)[4], int idx)
-{
-    const unsigned lo = (idx & 2) ? R[1] : R[0], hi = (idx & 2) ? R[3] : R[2];
-    const unsigned r = (idx & 4) ? hi : lo;
-    return __byte_perm(r, 0, (idx & 1) ? 0x4432 : 0x4410);
-}
-
 template <int G>
 __device__ __forceinline__ bool group_any(bool v)
 {
@@ -561,6 +554,12 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
     reset_state<PAD>(L, mm, padLane);
     const int umul = 100 - a.uniq;
     const unsigned kb = (unsigned)q * 8u;
+    // The winner's neighbours S[best -/+ 1] are read from a shared-memory copy of the pixel's sums (any lane can address
+    // any disparity there: no register picks, no index shuffles); two copies used in turn, one warp barrier per step.
+    __shared__ __align__(16) uint16_t sS[2][128 * 8];
+    uint16_t* smine = &sS[0][0] + threadIdx.x * 8;
+    const uint16_t* spix = &sS[0][0] + (threadIdx.x / G) * G * 8;
+    int alt = 0;
     // The per-pixel epilogue (parabola, division, scatter, store) is identical on all G lanes of a pixel, so it is
     // deferred: lane q keeps the winner of every G-th step and the G lanes finish G pixels at once.
     unsigned svKey = 0, svM = 0, svP = 0;
@@ -603,6 +602,7 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
             Sf[3] = __viaddmin_u16x2(Sq.w, L[3], MVSV_PK_MAX);
         }
         if (PAD && padLane) Sf[0] = Sf[1] = Sf[2] = Sf[3] = MVSV_PK_MAX;
+        st128(smine + alt, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
         if (a.storeS && active && mem) st128(sdbg + xi * Dp, make_uint4(Sf[0], Sf[1], Sf[2], Sf[3]));
         // ---- first argmin via (S << 16 | k) keys
         unsigned key = min(min((Sf[0] << 16) | kb, (Sf[0] & 0xffff0000u) | (kb + 1)),
@@ -614,7 +614,14 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
         const int minS = (int)(key >> 16);
         const int best = (int)(key & 0xffffu);
         bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
+        // ---- neighbours of the winner for the parabola
+        const int im = max(best - 1, 0), ip = min(best + 1, a.D - 1);
+        __syncwarp();
+        const unsigned vm = spix[alt + im], vp = spix[alt + ip];
+        alt ^= 128 * 8;
         if (a.uniq > 0) {
+            // (a packed count of the sums below floor((minS * 100 - 1) / (100 - uniq)) was measured slower: the division
+            // per step costs more than the eight multiply-compares)
             bool bad = false;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -623,13 +630,6 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
                 bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
             }
             reject |= group_any<G>(bad);
-        }
-        // ---- neighbours of the winner for the parabola
-        const int im = max(best - 1, 0), ip = min(best + 1, a.D - 1);
-        unsigned vm = pick16(Sf, im & 7), vp = pick16(Sf, ip & 7);
-        if (G > 1) {
-            vm = __shfl_sync(FULL, vm, im >> 3, G);
-            vp = __shfl_sync(FULL, vp, ip >> 3, G);
         }
         if (sc == q) { svKey = key; svM = vm; svP = vp; svX = reject ? -1 : xi; }
         if (++sc == G) { flush(); sc = 0; }
