@@ -465,7 +465,11 @@ def run_config(cx, key, batch, steps, warmup, detail=False):
            "kernel_ms_per_step": {k: v[0] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
            "sweep_strips_per_frame": eng.info.sgbm_td_cluster if spec["kind"] != "bm" else None,
            "s_volume": None if spec["kind"] == "bm" else ("u8 excess over npaths*C" if eng.info.sgbm_s8 else "u16"),
+           "bm_column_sums": None if spec["kind"] != "bm" else ("u8 (blockSize*2*cap <= 255)" if eng.info.bm_col8 else "u16"),
            "parity": parity}
+    if spec["kind"] == "bm":
+        # bytes the two volume kernels actually move per cell: the column sums written once and read once
+        out["roofline_path"]["step_bytes_per_cell"] = 2.0 if eng.info.bm_col8 else 4.0
     if detail:
         out["_detail"] = dict(s8=bool(eng.info.sgbm_s8), prof=prof, launches=launches, clocks=clocks, gen=gen, uniq=uniq, gpu_disp=gpu_disp,
                               cells=cells, fps=fps, fps_e2e=fps_e2e, ms_max=ms_max, ms_e2e_max=ms_e2e_max, d2h=d2h)

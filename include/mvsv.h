@@ -66,6 +66,8 @@ typedef struct mvsv_info {
     int last_batch;                  /* stereo pairs of the last compute == frames mvsv_download copies      */
     int sgbm_s8;                     /* the last SGBM compute kept the aggregated volume as one byte per cell
                                         (npaths * P2 <= 255: every path cost is C + e, 0 <= e <= P2)              */
+    int bm_col8;                     /* the StereoBM parameters keep the column-sum volume as one byte per cell
+                                        (blockSize * 2 * preFilterCap <= 255, e.g. configs/bm.yml: 21 * 4 = 84)   */
 } mvsv_info;
 
 /* Create an engine on CUDA device `device` for raw frames of frame_width x frame_height, holding up to
@@ -192,7 +194,7 @@ int mvsv_host_free(void* p);
  * 5 = BM prefiltered left, 6 = BM prefiltered right, 7 / 8 = fixed-point rectification map of camera 0 / 1
  * (roi_h x roi_w int32 pairs: x*32, y*32 rounded).  Returns bytes written or a negative error. */
 /* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
- * bit 1: never keep the aggregated volume as bytes (mvsv_info.sgbm_s8).
+ * bit 1: never keep a volume as bytes (mvsv_info.sgbm_s8, mvsv_info.bm_col8).
  * bits 8..15: force the number of column strips per frame of the fused sweep (0xff = force the independent passes,
  * 0xfe = force the sweep with the usual choice of strips: small batches otherwise take the independent passes). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);

@@ -43,7 +43,7 @@ class BmParams(C.Structure):
 class Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "frame_width", "frame_height", "width", "height", "max_batch", "sgbm_minX1", "sgbm_W1", "sgbm_D",
-        "sgbm_Dpad", "sgbm_npaths", "num_rois", "device", "sgbm_td_cluster", "last_batch", "sgbm_s8")]
+        "sgbm_Dpad", "sgbm_npaths", "num_rois", "device", "sgbm_td_cluster", "last_batch", "sgbm_s8", "bm_col8")]
 
 
 _lib = None

@@ -791,6 +791,7 @@ int mvsv_get_info(const mvsv_ctx* c, mvsv_info* info)
     info->num_rois = c->nrois; info->device = c->device; info->sgbm_td_cluster = c->has_sgbm ? c->td_nc : 0;
     info->last_batch = c->lastB;
     info->sgbm_s8 = c->last_s8 ? 1 : 0;
+    info->bm_col8 = (c->has_bm && c->bm.col8 && !(c->debug_flags & 2u)) ? 1 : 0;
     return MVSV_OK;
 }
 
