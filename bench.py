@@ -435,6 +435,8 @@ def run_config(cx, key, batch, steps, warmup, detail=False):
     eng.sync()
     ms_e2e = (time.perf_counter() - t0) * 1e3          # host clock between two device synchronisations
     fence()
+    if os.environ.get("MVSV_BENCH_DEBUG"):
+        print("[rank %d] %s: device %.3f ms/step, e2e %.3f ms/step" % (cx.rank, key, ms / steps, ms_e2e / steps), file=sys.stderr, flush=True)
     ms_e2e_max, frames_e2e = shard.reduce_max_and_sum(cx.dist, cx.dev, ms_e2e, B * steps)
     fps_e2e = frames_e2e / (ms_e2e_max * 1e-3)
     gpu_disp = hd[(steps - 1) & 1].array[:uniq].copy()
