@@ -77,21 +77,36 @@ def test_cuda_vs_oracle_random(oracle, case):
         assert np.array_equal(got, want), (p, H, W, seed, kind, hex(flags), int((got != want).sum()))
 
 
-@pytest.mark.gpu
-@settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck))
-@given(st.sampled_from([16, 32, 48, 64, 80]), st.sampled_from([5, 7, 9, 15, 21]), st.integers(1, 63),
-       st.sampled_from([0, 5, 15]), st.sampled_from([0, 10, 60]), st.integers(30, 60), st.integers(0, 999))
-def test_cuda_bm_vs_oracle_random(oracle, nd, bs, cap, uniq, tex, H, seed):
-    from mvstereovision3_b200 import api
+@st.composite
+def bm_case(draw):
+    """Random in-contract StereoBM parameters and shapes: every numDisp the contract allows, block sizes on both sides of
+    the window-ring limits, caps on both sides of the byte-volume limit (blockSize * 2 * cap <= 255), valid regions
+    from a single pixel up, two different frames per call."""
+    nd = draw(st.sampled_from([16, 32, 48, 64, 80, 96, 112, 128, 160, 208, 256]))
+    bs = draw(st.sampled_from([5, 7, 9, 11, 15, 21, 23, 25, 31, 41, 63]))
+    cap = draw(st.sampled_from([1, 2, 3, 6, 12, 31, 63]))
     if bs * bs * 2 * cap > 65535:
         cap = 65535 // (2 * bs * bs)
-    W = nd + bs + 40
-    H = max(H, bs + 8)
-    l, r, _ = synth.stereogram(H, W, 0, nd, seed=seed)
+    uniq = draw(st.sampled_from([0, 0, 5, 15, 40]))
+    tex = draw(st.sampled_from([0, 10, 60, 400]))
+    W = nd + bs - 1 + draw(st.sampled_from([1, 2, 3, 7, 19, 40, 77]))     # width1 - 2*w2 = that many valid columns
+    H = bs + draw(st.sampled_from([1, 2, 5, 13, 30]))                     # H - 2*w2 = that many + 1 valid rows (cv2 wants H > blockSize)
+    return nd, bs, cap, uniq, tex, H, W, draw(st.integers(0, 999)), draw(st.sampled_from([0, 2]))
+
+
+@pytest.mark.gpu
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@given(bm_case())
+def test_cuda_bm_vs_oracle_random(oracle, case):
+    from mvstereovision3_b200 import api
+    nd, bs, cap, uniq, tex, H, W, seed, flags = case
+    pairs = [synth.stereogram(H, W, 0, nd, seed=seed)[:2], synth.random_pair(H, W, seed=seed + 1)]
     p = dict(numDisp=nd, blockSize=bs, preFilterCap=cap, textureThreshold=tex, uniquenessRatio=uniq)
-    with api.Engine(W, H) as e:
+    with api.Engine(W, H, max_batch=2) as e:
         e.set_bm_params(**p)
-        e.compute(l, r, api.STAGE_BM)
-        got = e.download(1)["disp"][0]
-    want = oracle.bm(l, r, p)
-    assert np.array_equal(got, want), (p, H, W, seed, int((got != want).sum()))
+        e.debug_set_flags(flags)                     # 2: column sums 16 bits wide also where a byte would do
+        e.compute(np.stack([pairs[0][0], pairs[1][0]]), np.stack([pairs[0][1], pairs[1][1]]), api.STAGE_BM)
+        got = e.download(2)["disp"]
+    for b in range(2):
+        want = oracle.bm(pairs[b][0], pairs[b][1], p)
+        assert np.array_equal(got[b], want), (p, H, W, seed, flags, b, int((got[b] != want).sum()))
