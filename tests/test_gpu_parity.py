@@ -249,6 +249,26 @@ def test_cfg1_bm_full_size_vs_cv2():
     check("cfg1", d, m.compute(l, r))
 
 
+@pytest.mark.parametrize("nd,bs,cap,uniq,H,W,B", [(80, 21, 2, 0, 480, 752, 7), (256, 21, 31, 10, 1080, 1920, 2),
+                                                  (128, 11, 2, 5, 1080, 1920, 3)],
+                         ids=["bm_yml_batch7", "1080p_d256_u16", "1080p_d128_bytes"])
+def test_bm_batches_full_size_vs_cv2(nd, bs, cap, uniq, H, W, B):
+    """StereoBM at full sizes against cv2 live, several different frames per call (a warp's rows straddle frames):
+    configs/bm.yml, a 16-bit volume at D = 256 and a byte volume at D = 128."""
+    cv2 = _cv2()
+    p = dict(numDisp=nd, blockSize=bs, preFilterCap=cap, uniquenessRatio=uniq, textureThreshold=30)
+    m = cv2.StereoBM_create(numDisparities=nd, blockSize=bs)
+    m.setPreFilterCap(cap); m.setUniquenessRatio(uniq); m.setTextureThreshold(30)
+    frames = [synth.stereogram(H, W, 0, nd, seed=100 + b)[:2] for b in range(B)]
+    with api.Engine(W, H, max_batch=B) as e:
+        e.set_bm_params(**p)
+        assert e.info.bm_col8 == (1 if bs * 2 * cap <= 255 else 0)
+        e.compute(np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]), api.STAGE_BM)
+        out = e.download(B)["disp"]
+    for b in range(B):
+        check("bm full/%d" % b, out[b], m.compute(frames[b][0], frames[b][1]))
+
+
 def test_cfg3_pipeline(oracle):
     """remap(maps of parameters/baseline_small) -> crop -> SGBM cfg 2 -> XYZ -> 81 sub-image + sample-point means."""
     g = np.load(os.path.join(cases.GOLDEN_DIR, "rectify_baseline_small.npz"))
