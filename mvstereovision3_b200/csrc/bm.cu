@@ -24,32 +24,60 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Row-marching: a thread owns one column of BM_ROWS rows (an even count, so the row pairs of the reference's loop
-// never straddle two CTAs) and keeps the horizontal differences of the previous rows in registers.
-constexpr int BM_ROWS = 16;
+// Prefilter (x-Sobel, clipped to [-cap, cap], + cap).  The reference walks the rows in pairs; written out, every row is
+// out[y] = clip(d[y-1] + 2 d[y] + d[y+1]) with d[r] = p[r][x+1] - p[r][x-1], rows reflected at the top and the bottom
+// (-1 -> 1, H -> H-2), the first and last column and -- when H is odd -- the last row being the constant `cap`.
+// A lane owns four adjacent columns (one 32-bit load and store per row) of a band of BM_PF_ROWS rows; the neighbouring
+// bytes come from the adjacent lanes' words by shuffle.  The differences are kept as packed 16-bit pairs with a bias
+// of 256 (no negative halves: plain 32-bit adds / subtracts are exact), so a row costs ~7 instructions per pixel.
+constexpr int BM_PF_ROWS = 32;
 
 __global__ void __launch_bounds__(128)
 k_bm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch, int W, int H, int cap,
                uint8_t* __restrict__ o0, uint8_t* __restrict__ o1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * BM_ROWS, y1 = min(y0 + BM_ROWS, H);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xw = blockIdx.x * 128 + lane * 4;               // first of this lane's four columns
+    const int ya = (blockIdx.y * 4 + warp) * BM_PF_ROWS, yb = min(ya + BM_PF_ROWS, H);
+    if (ya >= H) return;                                      // whole warps only
     const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
-    if (x >= W) return;
-    const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
-    uint8_t* out = (im ? o1 : o0) + (size_t)f * H * pitch + x;
-    const bool inner = x > 0 && x < W - 1;
-    auto dx = [&](int r) -> int {                  // horizontal difference of row r (clamped into the image by the callers)
-        const uint8_t* p = img + (size_t)r * pitch + x;
-        return inner ? (int)p[1] - (int)p[-1] : 0;
+    const bool inrow = xw < (int)pitch;                       // pitch is a multiple of 16 bytes: the whole word is inside
+    const int xl = inrow ? xw : (int)pitch - 4;
+    const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch + xl;
+    uint8_t* out = (im ? o1 : o0) + (size_t)f * H * pitch + xl;
+    const bool nbL = lane == 0 && xw >= 4, nbR = lane == 31 && xw + 4 < (int)pitch;
+    unsigned keep = 0;                                        // bytes of inner columns (0 < x < W - 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (xw + k > 0 && xw + k < W - 1) keep |= 0xffu << (8 * k);
+    const unsigned capw = (unsigned)cap * 0x01010101u;
+    constexpr unsigned BIAS = 0x01000100u;
+    // packed biased differences of row r: (d[x0], d[x0+1]) and (d[x0+2], d[x0+3])
+    auto diffs = [&](int r, unsigned& d01, unsigned& d23) {
+        const uint8_t* p = img + (size_t)r * pitch;
+        const unsigned w = *reinterpret_cast<const unsigned*>(p);
+        unsigned wl = __shfl_up_sync(FULL, w, 1), wr = __shfl_down_sync(FULL, w, 1);
+        if (nbL) wl = *reinterpret_cast<const unsigned*>(p - 4);
+        if (nbR) wr = *reinterpret_cast<const unsigned*>(p + 4);
+        const unsigned F = __funnelshift_l(wl, w, 8);        // bytes x0-1, x0, x0+1, x0+2
+        const unsigned G = __funnelshift_r(w, wr, 24);       // bytes x0+3, x0+4, ...
+        const unsigned X = __byte_perm(F, 0, 0x4140), Y = __byte_perm(F, 0, 0x4342), Z = __byte_perm(G, 0, 0x4140);
+        d01 = Y + BIAS - X;
+        d23 = Z + BIAS - Y;
     };
-    auto clip = [&](int v) -> int { return v < -cap ? 0 : (v > cap ? 2 * cap : v + cap); };
-    // rows are processed in pairs (y, y + 1), y even: out[y] = d[r0] + 2 d[y] + d[y+1] with r0 = y-1 (y+1 at the top),
-    // out[y+1] = d[y] + 2 d[y+1] + d[r3] with r3 = y+2 (y at the bottom); an odd last row is the constant `cap`
-    for (int y = y0; y < y1; y += 2) {
-        if (y + 1 >= H) { out[(size_t)y * pitch] = (uint8_t)cap; break; }
-        const int d0 = dx(y > 0 ? y - 1 : y + 1), d1 = dx(y), d2 = dx(y + 1), d3 = dx(y < H - 2 ? y + 2 : y);
-        out[(size_t)y * pitch] = (uint8_t)(inner ? clip(d0 + 2 * d1 + d2) : cap);
-        out[(size_t)(y + 1) * pitch] = (uint8_t)(inner ? clip(d1 + 2 * d2 + d3) : cap);
+    const unsigned lo = (unsigned)(1024 - cap) * 0x10001u, hi = (unsigned)(1024 + cap) * 0x10001u;
+    unsigned p01, p23, c01, c23, n01, n23;
+    diffs(ya > 0 ? ya - 1 : 1, p01, p23);
+    diffs(ya, c01, c23);
+    for (int y = ya; y < yb; ++y) {
+        diffs(y + 1 < H ? y + 1 : H - 2, n01, n23);
+        const unsigned s01 = p01 + 2 * c01 + n01, s23 = p23 + 2 * c23 + n23;     // biased by 1024 per half
+        const unsigned q01 = __vminu2(__vmaxu2(s01, lo), hi) - lo, q23 = __vminu2(__vmaxu2(s23, lo), hi) - lo;
+        unsigned v = __byte_perm(q01, q23, 0x6420);
+        v = (v & keep) | (capw & ~keep);
+        if ((H & 1) && y == H - 1) v = capw;
+        if (inrow) *reinterpret_cast<unsigned*>(out + (size_t)y * pitch) = v;
+        p01 = c01; p23 = c23; c01 = n01; c23 = n23;
     }
 }
 
@@ -462,7 +490,7 @@ void launch_bm(mvsv_ctx* c, int B)
     const size_t npx = (size_t)B * W * H;
     { KernelTimer kt(c, KID_FILL); k_fill16<<<(unsigned)((npx / 8 + 256) / 256), 256, 0, c->stream>>>(c->disp, npx, (int16_t)n.FILT); }
     {
-        dim3 blk(128), grd((W + 127) / 128, (H + BM_ROWS - 1) / BM_ROWS, 2 * B);
+        dim3 blk(128), grd((W + 127) / 128, (H + 4 * BM_PF_ROWS - 1) / (4 * BM_PF_ROWS), 2 * B);
         KernelTimer kt(c, KID_BM_PREFILTER);
         k_bm_prefilter<<<grd, blk, 0, c->stream>>>(c->rect[0], c->rect[1], c->pitch, W, H, n.cap, c->bm_pre[0], c->bm_pre[1]);
     }
