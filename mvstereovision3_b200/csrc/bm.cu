@@ -81,11 +81,68 @@ k_bm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img
     }
 }
 
-// texture: window sum of |L - cap| over blockSize x blockSize pixels.  One CTA = 256 adjacent columns (256 - 2*w2 of them
-// produce output) x BM_TEX_ROWS rows: a thread slides the vertical sum of its column down the band; per row the CTA
-// turns the 256 column sums into inclusive prefix sums (shuffle scan per warp + the warps' totals) and an output pixel
-// is the difference of two of them.
+// texture: window sum of |L - cap| over blockSize x blockSize pixels.
+// k_bm_tex_w (blockSize <= 63): a warp owns 128 adjacent columns (128 - 2*w2 of them, rounded down to a multiple of
+// four, produce output) and a band of BM_TEX_ROWS rows; a lane slides the vertical sums of its four columns down the
+// band (VABSDIFF4 on the entering and the leaving word), the warp turns the 128 column sums of a row into inclusive
+// prefix sums (three adds per lane + a shuffle scan of the lanes' totals) in its own piece of shared memory, and an
+// output pixel is the difference of two of them.  No CTA barrier.
 constexpr int BM_TEX_ROWS = 64;
+__global__ void __launch_bounds__(128)
+k_bm_tex_w(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap, int* __restrict__ tex)
+{
+    __shared__ __align__(16) int pre[4][2][132];              // [warp][copy][1 + 128]: pre[..][0] = 0 stands for P[-1]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nxw = (128 - 2 * w2) & ~3;
+    const int X0 = blockIdx.x * nxw;                          // first column of this warp (a multiple of four)
+    const int ya = w2 + (blockIdx.y * 4 + warp) * BM_TEX_ROWS, yb = min(ya + BM_TEX_ROWS, H - w2);
+    if (ya >= yb) return;
+    const int xl = min(X0 + 4 * lane, (int)pitch - 4);        // (lanes past the row feed no output)
+    const uint8_t* p = preL + (size_t)blockIdx.z * H * pitch + xl;
+    const unsigned capw = (unsigned)cap * 0x01010101u;
+    unsigned s01 = 0, s23 = 0;                                // vertical sums of columns (0, 1) and (2, 3), packed u16x2
+    for (int dy = -w2; dy <= w2; ++dy) {
+        const unsigned a = __vabsdiffu4(*reinterpret_cast<const unsigned*>(p + (size_t)(ya + dy) * pitch), capw);
+        s01 += __byte_perm(a, 0, 0x4140); s23 += __byte_perm(a, 0, 0x4342);
+    }
+    int* P = &pre[warp][0][0];
+    if (lane == 0) { pre[warp][0][0] = 0; pre[warp][1][0] = 0; }
+    // this lane's output columns: local index j = 4 * lane + k in [w2, w2 + nxw), x = X0 + j < W - w2
+    const int j0 = 4 * lane;
+    int* o = tex + ((size_t)blockIdx.z * H + ya) * W + X0 + j0;
+    const uint8_t* pin = p + (size_t)(ya + w2 + 1) * pitch;   // rows entering / leaving the window of the next output row
+    const uint8_t* pout = p + (size_t)(ya - w2) * pitch;
+    int alt = 0;
+    for (int y = ya; y < yb; ++y) {
+        unsigned e = 0, f = 0;
+        if (y + 1 < yb) { e = *reinterpret_cast<const unsigned*>(pin); f = *reinterpret_cast<const unsigned*>(pout); pin += pitch; pout += pitch; }
+        const int t0 = (int)(s01 & 0xffffu), t1 = t0 + (int)(s01 >> 16), t2 = t1 + (int)(s23 & 0xffffu), t3 = t2 + (int)(s23 >> 16);
+        int v = t3;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(FULL, v, d);
+            if (lane >= d) v += u;
+        }
+        const int off = v - t3;                               // sum of the lanes to the left
+        int* Pc = P + alt * 132 + 1;
+        Pc[j0] = off + t0; Pc[j0 + 1] = off + t1; Pc[j0 + 2] = off + t2; Pc[j0 + 3] = off + t3;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = j0 + k;
+            if (j >= w2 && j < w2 + nxw && X0 + j < W - w2) o[k] = Pc[j + w2] - Pc[j - w2 - 1];
+        }
+        alt ^= 1;                                             // the next row writes the other copy: one warp barrier per row
+        o += W;
+        const unsigned ae = __vabsdiffu4(e, capw), af = __vabsdiffu4(f, capw);
+        s01 += __byte_perm(ae, 0, 0x4140) - __byte_perm(af, 0, 0x4140);
+        s23 += __byte_perm(ae, 0, 0x4342) - __byte_perm(af, 0, 0x4342);
+    }
+}
+
+// k_bm_tex (any blockSize): one CTA = 256 adjacent columns (256 - 2*w2 of them produce output) x BM_TEX_ROWS rows: a
+// thread slides the vertical sum of its column down the band; per row the CTA turns the 256 column sums into inclusive
+// prefix sums (shuffle scan per warp + the warps' totals) and an output pixel is the difference of two of them.
 __global__ void __launch_bounds__(256)
 k_bm_tex(const uint8_t* __restrict__ preL, size_t pitch, int W, int H, int w2, int cap, int* __restrict__ tex)
 {
@@ -497,10 +554,16 @@ void launch_bm(mvsv_ctx* c, int B)
     const bool any = !(n.lofs >= W || n.width1 < 1) && (H - 2 * n.w2 > 0) && (n.width1 - 2 * n.w2 > 0);
     if (!any) return;
     {
-        const int nx = 256 - 2 * n.w2;                      // blockSize <= 255: at least two output columns per CTA
-        dim3 grd((W - 2 * n.w2 + nx - 1) / nx, (H - 2 * n.w2 + BM_TEX_ROWS - 1) / BM_TEX_ROWS, B);
         KernelTimer kt(c, KID_BM_TEX);
-        k_bm_tex<<<grd, 256, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex2);
+        if (n.bs <= 63) {
+            const int nxw = (128 - 2 * n.w2) & ~3;
+            dim3 grd((W - 2 * n.w2 + nxw - 1) / nxw, (H - 2 * n.w2 + 4 * BM_TEX_ROWS - 1) / (4 * BM_TEX_ROWS), B);
+            k_bm_tex_w<<<grd, 128, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex2);
+        } else {
+            const int nx = 256 - 2 * n.w2;                  // blockSize <= 255: at least two output columns per CTA
+            dim3 grd((W - 2 * n.w2 + nx - 1) / nx, (H - 2 * n.w2 + BM_TEX_ROWS - 1) / BM_TEX_ROWS, B);
+            k_bm_tex<<<grd, 256, 0, c->stream>>>(c->bm_pre[0], c->pitch, W, H, n.w2, n.cap, c->bm_tex2);
+        }
     }
     {
         const long long threads = (long long)n.width1 * (n.D / 8);
