@@ -375,6 +375,10 @@ int mvsv_init(int device, int frame_width, int frame_height, int max_batch, mvsv
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (cudaEvent_t& ev : c->ev_chunk)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& sl : c->slot)
         if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (cudaEvent_t* ev : {&c->ev_h2d, &c->ev_done, &c->ev_order})
@@ -409,6 +413,10 @@ void mvsv_destroy(mvsv_ctx* c)
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     for (cudaEvent_t ev : {c->ev_h2d, c->ev_done, c->ev_order})
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->stream) cudaStreamDestroy(c->stream);

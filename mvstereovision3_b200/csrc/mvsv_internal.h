@@ -44,6 +44,11 @@ struct mvsv_ctx {
     // mvsv_order_after() has placed in front of this engine's kernels
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_order = nullptr;
+    // second kernel stream: the first row scan of one chunk of frames runs beside the cost kernel of the next chunk
+    // (sgbm.cu, launch_sgbm_g); joined back into `stream` before the sweep
+    cudaStream_t aux_stream = nullptr;
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t ev_chunk[kMaxChunks] = {}, ev_join = nullptr;
     int fw = 0, fh = 0;          // raw frame
     int W = 0, H = 0;            // rectified/cropped pair
     int maxB = 0;
@@ -131,7 +136,8 @@ struct mvsv_ctx {
 // RAII bracket: records CUDA events on the ctx stream around one kernel launch when profiling is on.
 struct KernelTimer {
     mvsv_ctx* c; int idx;
-    KernelTimer(mvsv_ctx* ctx, int kid) : c(ctx), idx(-1)
+    cudaStream_t st;
+    KernelTimer(mvsv_ctx* ctx, int kid, cudaStream_t on = nullptr) : c(ctx), idx(-1), st(on ? on : ctx->stream)
     {
         ++c->launches;
         if (!c->prof) return;
@@ -140,11 +146,11 @@ struct KernelTimer {
             if (!c->ev_free.empty()) { *e = c->ev_free.back(); c->ev_free.pop_back(); }
             else cudaEventCreate(e);
         }
-        cudaEventRecord(b.a, c->stream);
+        cudaEventRecord(b.a, st);
         c->brackets.push_back(b);
         idx = (int)c->brackets.size() - 1;
     }
-    ~KernelTimer() { if (idx >= 0) cudaEventRecord(c->brackets[idx].b, c->stream); }
+    ~KernelTimer() { if (idx >= 0) cudaEventRecord(c->brackets[idx].b, st); }
 };
 
 // ---- kernel launchers (launch counting happens in KernelTimer) ------------------------------------------

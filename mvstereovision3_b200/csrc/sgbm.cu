@@ -710,6 +710,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
                                               planeStrideR, c->vsRP, c->vsJOFF);
     }
     std::function<void(int, int)> launch_vsum;
+    int vsum_gx = 1;                                  // column strips (CTAs) of the cost kernel per frame
     auto make_vsum = [&](auto wideTag) {
         constexpr bool WIDE = decltype(wideTag)::value;
         using GE = VsGeom<G, WIDE>;
@@ -722,6 +723,7 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         const size_t smem = vsum_smem_bytes<G, WIDE>(2 * n.SH2 + 1, r8);
         // small batches: split the rows into bands until the grid covers the SMs (each band repeats bs-1 rows)
         const int gx = (n.W1 + PX - 1) / PX, bs = 2 * n.SH2 + 1;
+        vsum_gx = gx;
         int bands = 1;
         while (bands < 8 && (long long)gx * B * (bands * 2) <= c->num_sms && c->H / (bands * 2) >= 4 * bs) bands *= 2;
         a.bandRows = (c->H + bands - 1) / bands;
@@ -769,12 +771,38 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         const unsigned nall = (unsigned)n.npaths, kcl = (32767u + nall - 1) / nall;     // all paths, see k_sgbm_h2_wta
         a.nprevPk = nall * 0x10001u; a.kclampPk = kcl * 0x10001u;
     }
-    launch_vsum(0, B);
-    {
-        KernelTimer kt(c, KID_SGBM_H1);
+    // Cost kernel (shared-memory / ALU bound) and first row scan (HBM bound) of different chunks of frames side by side:
+    // chunk i's scan runs on the second stream while the cost kernel of chunk i + 1 runs on the engine's; joined before
+    // the sweep.  About seven chunks per batch, each at least ~0.9 waves of cost-kernel CTAs (measured, ms per step --
+    // cfg 2, frames per chunk 13 / 15 / 19 / 26 / all: 12.26 / 12.13 / 11.73 / 11.93 / 12.29; cfg 4, 2 / 3 / 4 / 5 / all:
+    // 35.9 / 36.3 / 36.0 / 37.0 / 37.2; cfg 5, 1 / 2 / 3 / all: 78.3 / 74.3 / 76.0 / 76.2; a higher stream priority for the
+    // scan: slower).
+    auto launch_h1 = [&](int f0, int nb, cudaStream_t on) {
+        AggArgs h = a;
+        const size_t off = (size_t)f0 * c->H * n.W1 * n.Dp;
+        h.VS += off; h.C += off; h.S += s8 ? off / 2 : off; h.B = nb;
+        const unsigned blocks = (unsigned)(((long long)nb * c->H * G + TPB - 1) / TPB);
+        KernelTimer kt(c, KID_SGBM_H1, on);
         const size_t sm = (size_t)(2 * n.SW2 + 1 + H1_PFD) * TPB * 16;
-        if (s8) k_sgbm_h1<G, PAD, true><<<rowBlocks, TPB, sm, st>>>(a);
-        else k_sgbm_h1<G, PAD, false><<<rowBlocks, TPB, sm, st>>>(a);
+        if (s8) k_sgbm_h1<G, PAD, true><<<blocks, TPB, sm, on>>>(h);
+        else k_sgbm_h1<G, PAD, false><<<blocks, TPB, sm, on>>>(h);
+    };
+    int fpc = std::max((B + 6) / 7, (int)(0.9 * c->num_sms / vsum_gx + 0.999));   // frames per chunk
+    if (const char* e = getenv("MVSV_VH_FRAMES")) fpc = std::max(1, atoi(e));    // (tuning hook)
+    const int nchunks = std::min((B + fpc - 1) / fpc, (int)mvsv_ctx::kMaxChunks);
+    if (nchunks <= 1) {
+        launch_vsum(0, B);
+        launch_h1(0, B, st);
+    } else {
+        for (int i = 0; i < nchunks; ++i) {
+            const int f0 = i * fpc, f1 = (i + 1 == nchunks) ? B : f0 + fpc;
+            launch_vsum(f0, f1 - f0);
+            cudaEventRecord(c->ev_chunk[i], st);
+            cudaStreamWaitEvent(c->aux_stream, c->ev_chunk[i], 0);
+            launch_h1(f0, f1 - f0, c->aux_stream);
+        }
+        cudaEventRecord(c->ev_join, c->aux_stream);
+        cudaStreamWaitEvent(st, c->ev_join, 0);
     }
     auto vdirs = [&](int bottomUp) {
         if (plan.NS > 0) {
