@@ -395,13 +395,21 @@ def run_config(cx, key, batch, steps, warmup, detail=False):
     sampler = ClockSampler(cx.local_rank) if (detail and cx.rank == 0) else None
     if sampler:
         sampler.start()
-    eng.profile_enable(True)
     l0 = eng.launch_count
     eng.timer_start()
     for _ in range(steps):
         step_device()
     ms = eng.timer_stop()
     launches = eng.launch_count - l0
+    fence()
+    # Per-kernel CUDA-event durations come from a second pass over the same K steps: with per-kernel timing enabled the
+    # engine runs its kernels one after the other (mvsv_profile_enable), while in the timed pass above the cost kernel
+    # and the first row scan of different chunks of frames overlap on two streams -- a kernel's duration only means
+    # something when it runs alone, so the kernel times add up to a little more than ms_per_step.
+    eng.profile_enable(True)
+    for _ in range(steps):
+        step_device()
+    eng.sync()
     prof = eng.profile_read()
     eng.profile_enable(False)
     fence()

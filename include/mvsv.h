@@ -177,7 +177,10 @@ unsigned long long mvsv_launch_count(const mvsv_ctx* ctx);
 /* CUDA-event timing on the ctx stream (the stream the kernels are launched on).  timer_start/stop bracket a
  * region; profile_enable(1) additionally brackets every kernel launch with events, and profile_read returns the
  * accumulated milliseconds and launch counts per kernel id since the last read (n >= number of kernel ids;
- * returns that number).  mvsv_kernel_name(id) names an id ("" past the end). */
+ * returns that number).  mvsv_kernel_name(id) names an id ("" past the end).  While per-kernel timing is enabled the
+ * engine launches its kernels one after the other; without it the SGBM cost kernel and the first row scan of
+ * different chunks of a batch run side by side on two streams (a little faster, but a kernel's duration then
+ * includes its neighbour's). */
 int mvsv_timer_start(mvsv_ctx* ctx);
 int mvsv_timer_stop(mvsv_ctx* ctx, float* ms);
 int mvsv_profile_enable(mvsv_ctx* ctx, int enable);
@@ -196,7 +199,9 @@ int mvsv_host_free(void* p);
 /* bit 0: keep the complete aggregated S volume (all paths) readable through mvsv_debug_read(which=1).
  * bit 1: never keep a volume as bytes (mvsv_info.sgbm_s8, mvsv_info.bm_col8).
  * bits 8..15: force the number of column strips per frame of the fused sweep (0xff = force the independent passes,
- * 0xfe = force the sweep with the usual choice of strips: small batches otherwise take the independent passes). */
+ * 0xfe = force the sweep with the usual choice of strips: small batches otherwise take the independent passes).
+ * bits 16..23: force the number of frames per chunk of the overlapped cost kernel / first row scan (0 = chosen by the
+ * engine: about seven chunks per batch, one chunk for small batches). */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
 long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
 

@@ -788,8 +788,9 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
         else k_sgbm_h1<G, PAD, false><<<blocks, TPB, sm, on>>>(h);
     };
     int fpc = std::max((B + 6) / 7, (int)(0.9 * c->num_sms / vsum_gx + 0.999));   // frames per chunk
-    if (const char* e = getenv("MVSV_VH_FRAMES")) fpc = std::max(1, atoi(e));    // (tuning hook)
-    const int nchunks = std::min((B + fpc - 1) / fpc, (int)mvsv_ctx::kMaxChunks);
+    if ((c->debug_flags >> 16) & 0xffu) fpc = (int)((c->debug_flags >> 16) & 0xffu);     // test hook: frames per chunk
+    // per-kernel timing (mvsv_profile_enable) runs the kernels one after the other: a duration only means something alone
+    const int nchunks = c->prof ? 1 : std::min((B + fpc - 1) / fpc, (int)mvsv_ctx::kMaxChunks);
     if (nchunks <= 1) {
         launch_vsum(0, B);
         launch_h1(0, B, st);

@@ -101,6 +101,30 @@ def test_bm_vs_oracle(oracle, golden, case, wide):
             check(name + "/golden/" + kind, out[b], golden["bm/%s/%s" % (name, kind)])
 
 
+@pytest.mark.parametrize("fpc", [1, 2, 3])
+@pytest.mark.parametrize("name", ["sgbm_yml_d64", "hh_cfg4_style", "d48_hh", "d128_shipped"])
+def test_chunked_cost_and_first_scan(oracle, name, fpc):
+    """The cost kernel and the first row scan of different chunks of frames run side by side on two streams at large
+    batches; the debug flag forces `fpc` frames per chunk here: five different frames, every stage of every frame
+    against the oracle, byte form of S and 16-bit form."""
+    _, p, H, W = next(c for c in cases.SGBM_CASES if c[0] == name)
+    B = 5
+    frames = [synth.random_pair(H, W, seed=50 + b) if b % 2 else synth.stereogram(H, W, max(p["minDisp"], 0), p["numDisp"], seed=50 + b)[:2]
+              for b in range(B)]
+    L, R = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+    for flags in (1, 3):
+        with api.Engine(W, H, max_batch=B) as e:
+            e.set_sgbm_params(**gpu_params(p))
+            e.debug_set_flags(flags | (0xfe << 8) | (fpc << 16))
+            e.compute(L, R, api.STAGE_SGBM)
+            out, Cg, Sg = e.download(B)["disp"], e.debug_read(0, B), e.debug_read(1, B)
+        for b in range(B):
+            disp, Cv, Sv, _ = oracle.sgbm(frames[b][0], frames[b][1], p, want_volumes=True)
+            check("%s/C/%d/%d" % (name, flags, b), Cg[b], Cv)
+            check("%s/S/%d/%d" % (name, flags, b), Sg[b], Sv)
+            check("%s/disp/%d/%d" % (name, flags, b), out[b], disp)
+
+
 def test_remap_vs_oracle_and_golden(oracle, golden):
     H, W = 96, 140
     for seed in range(3):
