@@ -593,7 +593,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(spec, det["gen"])
         ref.run(1)
-        fpw = 4 if ref.kind == "reference" else 2
+        fpw = 16 if ref.kind == "reference" else 2          # ~14 s of CPU work on 16 cores (cv2), bounded for the port
         dt, n, outs = ref.run(fpw)
         cpu = {"value": n / dt, "unit": "frames/s", "cores": ref.cores, "kind": ref.kind,
                "sample": "%d frames of the same workload, %s, %.1f s wall" % (n, ref.describe(), dt),
