@@ -790,7 +790,10 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     int fpc = std::max((B + 6) / 7, (int)(0.9 * c->num_sms / vsum_gx + 0.999));   // frames per chunk
     if ((c->debug_flags >> 16) & 0xffu) fpc = (int)((c->debug_flags >> 16) & 0xffu);     // test hook: frames per chunk
     // per-kernel timing (mvsv_profile_enable) runs the kernels one after the other: a duration only means something alone
-    const int nchunks = c->prof ? 1 : std::min((B + fpc - 1) / fpc, (int)mvsv_ctx::kMaxChunks);
+    // (MVSV_SERIAL=1 does the same for a whole process: under ncu every kernel runs alone anyway, and the chunked cost
+    // kernel then shows its partial waves without the scan that fills them)
+    static const bool serialEnv = [] { const char* e = getenv("MVSV_SERIAL"); return e && atoi(e) != 0; }();
+    const int nchunks = (c->prof || serialEnv) ? 1 : std::min((B + fpc - 1) / fpc, (int)mvsv_ctx::kMaxChunks);
     if (nchunks <= 1) {
         launch_vsum(0, B);
         launch_h1(0, B, st);
