@@ -202,6 +202,9 @@ int mvsv_host_free(void* p);
  * 0xfe = force the sweep with the usual choice of strips: small batches otherwise take the independent passes).
  * bits 16..23: force the number of frames per chunk of the overlapped cost kernel / first row scan (0 = chosen by the
  * engine: about seven chunks per batch, one chunk for small batches). */
+/* Environment variables read by the library (diagnostics only): MVSV_SERIAL=1 launches every kernel of a compute
+ * one after the other (as per-kernel timing does) -- for profilers, which serialise kernels anyway; MVSV_NO_DSM=1
+ * sends the sweep's border records through global memory also where a thread-block cluster would be used. */
 int mvsv_debug_set_flags(mvsv_ctx* ctx, unsigned flags);
 long long mvsv_debug_read(mvsv_ctx* ctx, int which, void* host, size_t capacity_bytes);
 

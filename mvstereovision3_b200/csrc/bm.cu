@@ -1,16 +1,16 @@
 // StereoBM (PREFILTER_XSOBEL, minDisparity 0) on sm_100a -- replaces cv::StereoBM::compute behind
 // Disparity::bm (reference src/disparity.cpp:18-22, parameters configs/bm.yml).  Semantics: SURVEY.md A.4.
 //
-//   pre[img][B][H][pitch] u8      : x-Sobel prefiltered images
-//   col[B][H][width1][Dp] u16     : column sums  sum_dy |L[y+dy][x'+lofs] - R[y+dy][x'+k]|
-//   tex[B][H][W] int              : window sums of |L - cap| (texture)
-// The horizontal box sum of `col`, winner-take-all, texture/uniqueness tests and the sub-pixel step are
-// fused in one row-marching kernel with the same 8-values-per-lane packed u16x2 layout as SGBM.
+//   pre[img][B][H][pitch] u8        : x-Sobel prefiltered images                                   (k_bm_prefilter)
+//   tex[B][H][W] int                : window sums of |L - cap| (texture)                           (k_bm_tex_w / k_bm_tex)
+//   col[B][H][width1][D] u16 or u8  : column sums  sum_dy |L[y+dy][x'+lofs] - R[y+dy][x'+k]|       (k_bm_colsum)
+//                                     one byte per cell while blockSize * 2 * cap <= 255 (configs/bm.yml: 84)
+// The horizontal window sum of `col`, winner-take-all, texture / uniqueness tests and the sub-pixel step are fused in
+// one row-marching kernel (k_bm_wta) that reads every column of the volume from HBM once (window ring in shared
+// memory).  DESIGN.md section 4 "StereoBM" has the measurements behind each choice.
 #include "mvsv_internal.h"
 
 #include <algorithm>
-
-#include <cstdlib>
 
 namespace {
 
