@@ -35,62 +35,123 @@ constexpr int vs_compute_threads(int G) { return G >= 8 ? 512 : 256; }
 //                  "address ascending" and every CTA's first entry is 16-byte aligned;
 //   left image  -> one 8-byte record per pixel (a_s, lo_s, hi_s, a_r, lo_r, hi_r, 0, 0).
 // ------------------------------------------------------------------------------------------------
-// Each warp covers 28 output columns (lanes 2..29; the outer two lanes on either side only feed neighbours) and
-// marches down PF_ROWS rows, loading one byte per lane per row: with s(x) = r0[x] + 2 r1[x] + r2[x] the Sobel
-// response is s(x+1) - s(x-1), so the horizontal taps come from shuffles and the vertical ones from registers.
-constexpr int PF_ROWS = 16, PF_COLS = 28, PF_WARPS = 4;
+// A lane owns four adjacent columns (one 32-bit load per row; lanes 1..30 of a warp produce output, the outer two only
+// feed their neighbours) and marches down PF_ROWS rows.  With s(x) = r0[x] + 2 r1[x] + r2[x] the Sobel response is
+// s(x+1) - s(x-1); values are kept as packed 16-bit pairs BY POSITION -- (x-1, x), (x+1, x+2), (x+3, x+4) relative to
+// the lane's first column -- one set per channel: the pairs of the neighbouring positions are then exactly the
+// registers a pixel pair's left / right neighbours live in, and only the centre pairs need a permute.  Every position
+// x <= 0 or x >= W-1 holds ftzero in both channels (the reference's border rule): the half-sample bounds of the first
+// and last column then come out right without a special case ((ftzero + ftzero) >> 1 = ftzero).
+constexpr int PF_ROWS = 16, PF_COLS = 120, PF_WARPS = 4;
+
+__device__ __forceinline__ unsigned pf_lo2(unsigned w) { return __byte_perm(w, 0, 0x4140); }     // bytes 0, 1 as a u16 pair
+__device__ __forceinline__ unsigned pf_hi2(unsigned w) { return __byte_perm(w, 0, 0x4342); }     // bytes 2, 3
+
+// centre pairs, lower and upper half-sample bounds of four pixels of one channel from its three position pairs
+__device__ __forceinline__ void pf_bounds(unsigned Pm, unsigned P1, unsigned P3, unsigned (&A)[2], unsigned (&LO)[2], unsigned (&HI)[2])
+{
+    A[0] = __byte_perm(Pm, P1, 0x5432); A[1] = __byte_perm(P1, P3, 0x5432);
+    // (a + neighbour) >> 1 per half: the sums stay below 2^9, so a plain add and a masked shift are exact
+    const unsigned ml0 = ((A[0] + Pm) >> 1) & 0x7fff7fffu, mr0 = ((A[0] + P1) >> 1) & 0x7fff7fffu;
+    const unsigned ml1 = ((A[1] + P1) >> 1) & 0x7fff7fffu, mr1 = ((A[1] + P3) >> 1) & 0x7fff7fffu;
+    LO[0] = __vimin3_u16x2(A[0], ml0, mr0); HI[0] = __vimax3_u16x2(A[0], ml0, mr0);
+    LO[1] = __vimin3_u16x2(A[1], ml1, mr1); HI[1] = __vimax3_u16x2(A[1], ml1, mr1);
+}
 
 __global__ void __launch_bounds__(PF_WARPS * 32)
 k_sgbm_prefilter(const uint8_t* __restrict__ img0, const uint8_t* __restrict__ img1, size_t pitch,
                  int W, int H, int ftzero, uint2* __restrict__ recL, uint16_t* __restrict__ plR,
-                 size_t planeStrideR, int RP, int JOFF)
+                 size_t planeStrideR, int RP, int JOFF, int ncx, int nbands)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = (blockIdx.x * PF_WARPS + warp) * PF_COLS + lane - 2;
-    const int y0 = blockIdx.y * PF_ROWS, y1 = min(y0 + PF_ROWS, H);
-    const int f = blockIdx.z >> 1, im = blockIdx.z & 1;
-    const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch;
-    const int xc = min(max(x, 0), W - 1);                       // out-of-image lanes load a valid byte, results unused
-    const bool inimg = x >= 0 && x < W, border = x <= 0 || x >= W - 1;
-    const bool writer = inimg && lane >= 2 && lane < 2 + PF_COLS;
-    int p0 = img[(size_t)max(y0 - 1, 0) * pitch + xc], p1 = img[(size_t)y0 * pitch + xc];
-    // both channels ride in one register (low half: clipped Sobel, high half: raw), so the half-sample bounds of the
-    // two channels cost one set of packed operations; per-row addresses advance by constants
-    const bool hasL = x > 0, hasR = x < W - 1;
-    const unsigned ftz2 = (unsigned)ftzero * 0x10001u;
-    uint2* rec = recL + ((size_t)f * H + y0) * W + xc;
-    uint16_t* o = plR + ((size_t)f * H + y0) * RP + (JOFF + W - 1 - xc);
-    // the row below is loaded one iteration ahead, so no iteration waits for its own load
-    const uint8_t* nxt = img + (size_t)min(y0 + 1, H - 1) * pitch + xc;
-    int pn = *nxt;
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * PF_WARPS + (threadIdx.x >> 5);          // warp -> (column chunk, row band)
+    const int band = gw / ncx, cx = gw - band * ncx;
+    if (band >= nbands) return;                                         // whole warps only
+    const int x0 = cx * PF_COLS + 4 * (lane - 1);                       // this lane's first column (a multiple of 4)
+    const int y0 = band * PF_ROWS, y1 = min(y0 + PF_ROWS, H);
+    const int f = blockIdx.y >> 1, im = blockIdx.y & 1;
+    // columns outside the row load some valid word instead: every position they feed is a border position
+    const int xl = min(max(x0, 0), (int)pitch - 4);
+    const uint8_t* img = (im ? img1 : img0) + (size_t)f * H * pitch + xl;
+    auto ldw = [&](int y) { return *reinterpret_cast<const unsigned*>(img + (size_t)min(max(y, 0), H - 1) * pitch); };
+    auto keep = [&](int xa) -> unsigned {       // halves of the pair (xa, xa + 1) that are not border positions
+        return ((xa > 0 && xa < W - 1) ? 0xffffu : 0u) | ((xa + 1 > 0 && xa + 1 < W - 1) ? 0xffff0000u : 0u);
+    };
+    const unsigned km = keep(x0 - 1), k1 = keep(x0 + 1), k3 = keep(x0 + 3);
+    const unsigned ftzp = (unsigned)ftzero * 0x10001u;
+    const unsigned fm = ftzp & ~km, f1 = ftzp & ~k1, f3 = ftzp & ~k3;
+    constexpr unsigned BIAS = 0x08000800u;                              // 2048 per half: the differences stay positive
+    const unsigned clo = (unsigned)(2048 - ftzero) * 0x10001u, chi = (unsigned)(2048 + ftzero) * 0x10001u;
+    const bool outLane = lane >= 1 && lane <= 30 && x0 < W;
+    const bool full = outLane && x0 + 3 < W;                            // all four columns inside the image
+    const bool vecL = (W & 1) == 0;                                     // four records = two aligned 16-byte stores
+    const int alignR = (JOFF + W) & 3;                                  // 0: 8-byte stores into the planes, 2: 4-byte, odd: 2-byte
+    const size_t rowsF = (size_t)f * H;
+
+    unsigned wb = ldw(y0), wc = ldw(y0 + 1);
+    unsigned a01, a23, b01 = pf_lo2(wb), b23 = pf_hi2(wb);
+    { const unsigned wa = ldw(y0 - 1); a01 = pf_lo2(wa); a23 = pf_hi2(wa); }
     for (int y = y0; y < y1; ++y) {
-        const int p2 = pn;
-        if (y + 2 < H) nxt += pitch;
-        pn = *nxt;                                              // row min(y + 2, H - 1)
-        const int sv = p0 + 2 * p1 + p2;
-        const int sl = __shfl_up_sync(FULL, sv, 1), sr = __shfl_down_sync(FULL, sv, 1);
-        const unsigned sob = (unsigned)(max(-ftzero, min(ftzero, sr - sl)) + ftzero);
-        const unsigned A = border ? ftz2 : (sob | ((unsigned)p1 << 16));
-        const unsigned l = __shfl_up_sync(FULL, A, 1), r = __shfl_down_sync(FULL, A, 1);
-        // (a + neighbour) >> 1 per half: the sums stay below 2^9, so a plain add and a masked shift are exact
-        const unsigned ml = hasL ? (((A + l) >> 1) & 0x7fff7fffu) : A;
-        const unsigned mr = hasR ? (((A + r) >> 1) & 0x7fff7fffu) : A;
-        const unsigned LO = __vminu2(A, __vminu2(ml, mr)), HI = __vmaxu2(A, __vmaxu2(ml, mr));
-        if (writer) {
+        const unsigned wn = ldw(y + 2);                                 // two rows ahead: consumed at the end of the iteration
+        const unsigned c01 = pf_lo2(wc), c23 = pf_hi2(wc);
+        const unsigned S01 = a01 + 2 * b01 + c01, S23 = a23 + 2 * b23 + c23;    // s(x0), s(x0+1) | s(x0+2), s(x0+3)
+        const unsigned Sm = __shfl_up_sync(FULL, S23, 1), Sp = __shfl_down_sync(FULL, S01, 1);
+        // clipped Sobel + ftzero at the positions (x0-1, x0), (x0+1, x0+2), (x0+3, x0+4)
+        unsigned sm = __vminu2(__vmaxu2(S01 + BIAS - Sm, clo), chi) - clo;
+        unsigned s1 = __vminu2(__vmaxu2(S23 + BIAS - S01, clo), chi) - clo;
+        unsigned s3 = __vminu2(__vmaxu2(Sp + BIAS - S23, clo), chi) - clo;
+        // raw channel at the same positions
+        const unsigned wl = __shfl_up_sync(FULL, wb, 1), wr = __shfl_down_sync(FULL, wb, 1);
+        const unsigned F = __funnelshift_l(wl, wb, 8), Gw = __funnelshift_r(wb, wr, 24);
+        unsigned rm = pf_lo2(F), r1 = pf_hi2(F), r3 = pf_lo2(Gw);
+        sm = (sm & km) | fm; s1 = (s1 & k1) | f1; s3 = (s3 & k3) | f3;
+        rm = (rm & km) | fm; r1 = (r1 & k1) | f1; r3 = (r3 & k3) | f3;
+        unsigned As[2], Ls[2], Hs[2], Ar[2], Lr[2], Hr[2];
+        pf_bounds(sm, s1, s3, As, Ls, Hs);
+        pf_bounds(rm, r1, r3, Ar, Lr, Hr);
+        if (outLane) {
             if (im == 0) {
-                // bytes: a_s lo_s hi_s a_r | lo_r hi_r 0 0
-                const unsigned w0 = __byte_perm(__byte_perm(A, LO, 0x2040), HI, 0x3410);
-                const unsigned w1 = __byte_perm(LO, HI, 0x4462) & 0xffffu;
-                *rec = make_uint2(w0, w1);
+                // record of a pixel: bytes a_s lo_s hi_s a_r | lo_r hi_r 0 0
+                uint2 rec[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned T1 = __byte_perm(As[h], Ls[h], 0x6240), T2 = __byte_perm(Hs[h], Ar[h], 0x6240);
+                    const unsigned T3 = __byte_perm(Lr[h], Hr[h], 0x6240);
+                    rec[2 * h] = make_uint2(__byte_perm(T1, T2, 0x5410), T3 & 0xffffu);
+                    rec[2 * h + 1] = make_uint2(__byte_perm(T1, T2, 0x7632), T3 >> 16);
+                }
+                uint2* dst = recL + (rowsF + y) * W + x0;
+                if (full && vecL) {
+                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(rec[0].x, rec[0].y, rec[1].x, rec[1].y);
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(rec[2].x, rec[2].y, rec[3].x, rec[3].y);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (x0 + k < W) dst[k] = rec[k];
+                }
             } else {
-                o[0 * planeStrideR] = (uint16_t)(A & 0xffffu); o[1 * planeStrideR] = (uint16_t)(LO & 0xffffu);
-                o[2 * planeStrideR] = (uint16_t)(0u - (HI & 0xffffu));
-                o[3 * planeStrideR] = (uint16_t)(A >> 16); o[4 * planeStrideR] = (uint16_t)(LO >> 16);
-                o[5 * planeStrideR] = (uint16_t)(0u - (HI >> 16));
+                // planes a_s, lo_s, -hi_s, a_r, lo_r, -hi_r, reversed in x: columns x0+3 .. x0 at indices j0-3 .. j0
+                const unsigned V[6][2] = {{As[0], As[1]}, {Ls[0], Ls[1]}, {__vneg2(Hs[0]), __vneg2(Hs[1])},
+                                          {Ar[0], Ar[1]}, {Lr[0], Lr[1]}, {__vneg2(Hr[0]), __vneg2(Hr[1])}};
+                uint16_t* o = plR + (rowsF + y) * RP + (JOFF + W - 1 - x0);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    uint16_t* op = o + (size_t)k * planeStrideR;
+                    const unsigned lo = __byte_perm(V[k][1], 0, 0x1032), hi = __byte_perm(V[k][0], 0, 0x1032);    // (x0+3, x0+2), (x0+1, x0)
+                    if (full && alignR == 0) {
+                        *reinterpret_cast<uint2*>(op - 3) = make_uint2(lo, hi);
+                    } else if (full && alignR == 2) {
+                        *reinterpret_cast<unsigned*>(op - 3) = lo; *reinterpret_cast<unsigned*>(op - 1) = hi;
+                    } else {
+                        if (x0 < W) op[0] = (uint16_t)(V[k][0] & 0xffffu);
+                        if (x0 + 1 < W) op[-1] = (uint16_t)(V[k][0] >> 16);
+                        if (x0 + 2 < W) op[-2] = (uint16_t)(V[k][1] & 0xffffu);
+                        if (x0 + 3 < W) op[-3] = (uint16_t)(V[k][1] >> 16);
+                    }
+                }
             }
         }
-        rec += W; o += RP;
-        p0 = p1; p1 = p2;
+        a01 = b01; a23 = b23; b01 = c01; b23 = c23; wb = wc; wc = wn;
     }
 }
 
@@ -704,10 +765,11 @@ void launch_sgbm_g(mvsv_ctx* c, int B)
     cudaStream_t st = c->stream;
     const size_t planeStrideR = (size_t)c->maxB * c->H * c->vsRP;
     {
-        dim3 blk(PF_WARPS * 32), grd((c->W + PF_WARPS * PF_COLS - 1) / (PF_WARPS * PF_COLS), (c->H + PF_ROWS - 1) / PF_ROWS, 2 * B);
+        const int ncx = (c->W + PF_COLS - 1) / PF_COLS, nbands = (c->H + PF_ROWS - 1) / PF_ROWS;
+        dim3 blk(PF_WARPS * 32), grd((ncx * nbands + PF_WARPS - 1) / PF_WARPS, 2 * B);
         KernelTimer kt(c, KID_SGBM_PREFILTER);
         k_sgbm_prefilter<<<grd, blk, 0, st>>>(c->rect[0], c->rect[1], c->pitch, c->W, c->H, n.ftzero, c->recL, c->plR,
-                                              planeStrideR, c->vsRP, c->vsJOFF);
+                                              planeStrideR, c->vsRP, c->vsJOFF, ncx, nbands);
     }
     std::function<void(int, int)> launch_vsum;
     int vsum_gx = 1;                                  // column strips (CTAs) of the cost kernel per frame
