@@ -343,7 +343,7 @@ k_ccl_apply(const int16_t* __restrict__ img, int16_t* __restrict__ out, const in
 // K8: reprojection (Utility::calcCoordinate over dmap2pcl's loop, reference src/utility.cpp:176-200,
 // 242-262) and per-ROI mean disparity (Utility::calcMeanDisparity, src/utility.cpp:265-285).
 // ------------------------------------------------------------------------------------------------
-struct QMat { float q[16]; };
+struct QMat { double q[16]; };     // the CV_32F matrix, widened on the host (cv::Mat_<float> products accumulate in double)
 
 // One thread = four consecutive pixels of the batch's linear pixel index: one 8-byte load, three 16-byte stores.
 __global__ void __launch_bounds__(256) k_xyz(const int16_t* __restrict__ disp, float* __restrict__ xyz, int W, int H, size_t npx, QMat Q)
@@ -359,26 +359,30 @@ __global__ void __launch_bounds__(256) k_xyz(const int16_t* __restrict__ disp, f
     }
     const size_t row = i0 / W;
     int x = (int)(i0 - row * W), y = (int)(row % H);
+    double dx = (double)x, dy = (double)y;                  // exact: the reference's float coordinates are integers < 2^24
     float o[12];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float value = (float)v4[k];
         float X = 0.f, Y = 0.f, Z = 0.f;
         if (value > 0.f) {
-            const float in[4] = {(float)x, (float)y, value / 16.f, 1.f};
+            const double dd = (double)(value / 16.f);
             float cc[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                double acc = 0.0;   // cv::Mat_<float> product accumulates in double
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc += (double)Q.q[r * 4 + j] * (double)in[j];
+                // ((((0 + q0 x) + q1 y) + q2 d) + q3 1): every product of two floats is exact in double, one rounding per add
+                double acc = Q.q[r * 4] * dx;
+                acc = __fma_rn(Q.q[r * 4 + 1], dy, acc);
+                acc = __fma_rn(Q.q[r * 4 + 2], dd, acc);
+                acc += Q.q[r * 4 + 3];
                 cc[r] = (float)acc;
             }
             X = cc[0] / cc[3]; Y = cc[1] / cc[3]; Z = cc[2] / cc[3];
             if (isinf(Z / 1000.f)) Z = 0.f;
         }
         o[3 * k] = X; o[3 * k + 1] = Y; o[3 * k + 2] = Z;
-        if (++x == W) { x = 0; if (++y == H) y = 0; }
+        dx += 1.0;
+        if (++x == W) { x = 0; dx = 0.0; if (++y == H) y = 0; dy = (double)y; }
     }
     float* dst = xyz + i0 * 3;
     if (i0 + 3 < npx) {
@@ -514,7 +518,7 @@ void launch_speckle(mvsv_ctx* c, const int16_t* img, int16_t* out, int B, int ne
 void launch_xyz(mvsv_ctx* c, int B)
 {
     QMat Q;
-    for (int i = 0; i < 16; ++i) Q.q[i] = c->Q[i];
+    for (int i = 0; i < 16; ++i) Q.q[i] = (double)c->Q[i];
     const size_t npx = (size_t)B * c->H * c->W;
     KernelTimer kt(c, KID_XYZ);
     k_xyz<<<(unsigned)((npx / 4 + 256) / 256), 256, 0, c->stream>>>(c->disp, c->xyz, c->W, c->H, npx, Q);
