@@ -1,5 +1,7 @@
 // Rectification (K1), 3x3 median (K5), speckle filter (K6), reprojection + ROI means (K8) on sm_100a.
 #include "mvsv_internal.h"
+
+#include <cstdint>
 #include <cfloat>
 #include <cmath>
 
@@ -166,6 +168,56 @@ k_median3(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int 
         const int hiL = __shfl_up_sync(0xffffffffu, hi, 1), hiR = __shfl_down_sync(0xffffffffu, hi, 1);
         const int m = med3i(max(lo, max(loL, loR)), med3i(mid, miL, miR), min(hi, min(hiL, hiR)));
         if (writer) dst[(size_t)y * W + x] = (int16_t)m;
+        p0 = p1; p1 = p2;
+    }
+}
+
+// Four columns per lane (W % 4 == 0: one 8-byte load and store per row), packed signed 16x2 arithmetic, values as pairs by
+// position as in the SGBM prefilter: the sorted triples of the columns (x0-1, x0) and (x0+1, x0+2), (x0+3, x0+4) are
+// one permute away from the lane's own pairs and its neighbours'.  Lanes 1..30 of a warp produce output.
+constexpr int MED4_COLS = 120;
+__device__ __forceinline__ unsigned med3s2(unsigned a, unsigned b, unsigned c)
+{
+    return __vmaxs2(__vmins2(a, b), __vmins2(__vmaxs2(a, b), c));
+}
+
+__global__ void __launch_bounds__(MED_WARPS * 32)
+k_median3_w4(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int H, int ncx, int nbands)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * MED_WARPS + (threadIdx.x >> 5);
+    const int band = gw / ncx, cx = gw - band * ncx;
+    if (band >= nbands) return;                                         // whole warps only
+    const int x0 = cx * MED4_COLS + 4 * (lane - 1);
+    const int y0 = band * MED_ROWS, y1 = min(y0 + MED_ROWS, H);
+    const int xl = min(max(x0, 0), W - 4);                              // lanes outside the row only feed edge lanes, which replicate
+    const int16_t* img = in + (size_t)blockIdx.y * W * H + xl;
+    int16_t* dst = out + (size_t)blockIdx.y * W * H + xl;
+    const bool writer = lane >= 1 && lane <= 30 && x0 < W;
+    const bool first = x0 == 0, last = x0 + 4 == W;
+    auto ld = [&](int y) { return *reinterpret_cast<const uint2*>(img + (size_t)min(max(y, 0), H - 1) * W); };
+    uint2 p0 = ld(y0 - 1), p1 = ld(y0);
+    for (int y = y0; y < y1; ++y) {
+        const uint2 p2 = ld(y + 1);
+        // sorted column triples of the lane's pairs (x0, x0+1) and (x0+2, x0+3)
+        const unsigned lo0 = __vimin3_s16x2(p0.x, p1.x, p2.x), hi0 = __vimax3_s16x2(p0.x, p1.x, p2.x), mi0 = med3s2(p0.x, p1.x, p2.x);
+        const unsigned lo1 = __vimin3_s16x2(p0.y, p1.y, p2.y), hi1 = __vimax3_s16x2(p0.y, p1.y, p2.y), mi1 = med3s2(p0.y, p1.y, p2.y);
+        unsigned res[2];
+        // neighbours' pairs: (x0-1, x0) from the previous lane's second pair, (x0+3, x0+4) towards the next lane's first
+        auto side = [&](unsigned q0, unsigned q1, unsigned& L0, unsigned& R0, unsigned& R1) {
+            const unsigned qm = __shfl_up_sync(0xffffffffu, q1, 1), qp = __shfl_down_sync(0xffffffffu, q0, 1);
+            L0 = first ? __byte_perm(q0, 0, 0x1010) : __byte_perm(qm, q0, 0x5432);      // replicate border
+            R0 = __byte_perm(q0, q1, 0x5432);                                          // (x0+1, x0+2): also the left of pair 1
+            R1 = last ? __byte_perm(q1, 0, 0x3232) : __byte_perm(q1, qp, 0x5432);
+        };
+        unsigned loL, loM, loR, miL, miM, miR, hiL, hiM, hiR;
+        side(lo0, lo1, loL, loM, loR);
+        side(mi0, mi1, miL, miM, miR);
+        side(hi0, hi1, hiL, hiM, hiR);
+        // median9 = med3(max of the minima, med of the medians, min of the maxima)
+        res[0] = med3s2(__vimax3_s16x2(lo0, loL, loM), med3s2(mi0, miL, miM), __vimin3_s16x2(hi0, hiL, hiM));
+        res[1] = med3s2(__vimax3_s16x2(lo1, loM, loR), med3s2(mi1, miM, miR), __vimin3_s16x2(hi1, hiM, hiR));
+        if (writer) *reinterpret_cast<uint2*>(dst + (size_t)y * W) = make_uint2(res[0], res[1]);
         p0 = p1; p1 = p2;
     }
 }
@@ -494,8 +546,14 @@ void launch_resize(mvsv_ctx* c, int cam, int B)
 
 void launch_median(mvsv_ctx* c, const int16_t* in, int16_t* out, int B)
 {
-    dim3 blk(MED_WARPS * 32), grd((c->W + MED_WARPS * MED_COLS - 1) / (MED_WARPS * MED_COLS), (c->H + MED_ROWS - 1) / MED_ROWS, B);
     KernelTimer kt(c, KID_MEDIAN);
+    if (c->W % 4 == 0 && c->W >= 4 && (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 8 == 0) {
+        const int ncx = (c->W + MED4_COLS - 1) / MED4_COLS, nbands = (c->H + MED_ROWS - 1) / MED_ROWS;
+        dim3 grd((ncx * nbands + MED_WARPS - 1) / MED_WARPS, B);
+        k_median3_w4<<<grd, MED_WARPS * 32, 0, c->stream>>>(in, out, c->W, c->H, ncx, nbands);
+        return;
+    }
+    dim3 blk(MED_WARPS * 32), grd((c->W + MED_WARPS * MED_COLS - 1) / (MED_WARPS * MED_COLS), (c->H + MED_ROWS - 1) / MED_ROWS, B);
     k_median3<<<grd, blk, 0, c->stream>>>(in, out, c->W, c->H);
 }
 
