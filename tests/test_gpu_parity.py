@@ -125,6 +125,27 @@ def test_chunked_cost_and_first_scan(oracle, name, fpc):
             check("%s/disp/%d/%d" % (name, flags, b), out[b], disp)
 
 
+@pytest.mark.parametrize("W", [16, 17, 18, 19, 20, 21, 22, 23, 119, 120, 121, 122, 123, 124, 125, 239, 240, 241, 244])
+def test_widths_around_the_lane_tiling(oracle, W):
+    """The prefilter and the median handle four columns per lane and 120 columns per warp (vector path when the width
+    allows it, scalar tails otherwise): every width class around those tilings, two heights, every stage."""
+    p = cases.sgbm_params(numDisp=8, blockSize=3, P1=7, P2=40, uniquenessRatio=5, speckleWindowSize=20, speckleRange=2)
+    for H in (5, 33):
+        pair = [synth.random_pair(H, W, seed=W + b) for b in range(2)]
+        with api.Engine(W, H, max_batch=2) as e:
+            e.set_sgbm_params(**gpu_params(p))
+            e.debug_set_flags(1)
+            e.compute(np.stack([pair[0][0], pair[1][0]]), np.stack([pair[0][1], pair[1][1]]), api.STAGE_SGBM)
+            out = e.download(2)["disp"]
+            Cg, raw, med = (e.debug_read(w, 2) for w in (0, 2, 4))
+        for b in range(2):
+            disp, Cv, Sv, rawv = oracle.sgbm(pair[b][0], pair[b][1], p, want_volumes=True, want_raw=True)
+            check("C/%d/%d" % (H, b), Cg[b], Cv)
+            check("raw/%d/%d" % (H, b), raw[b], rawv)
+            check("median/%d/%d" % (H, b), med[b], oracle.median3(rawv))
+            check("disp/%d/%d" % (H, b), out[b], disp)
+
+
 def test_remap_vs_oracle_and_golden(oracle, golden):
     H, W = 96, 140
     for seed in range(3):
