@@ -417,9 +417,14 @@ __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const u
     unsigned n3 = __vimin3_u16x2(X3, X4, __vminu2(L[3], mP2)) + C.w - mm;
     if (PAD && padLane) { n0 = n1 = n2 = n3 = MVSV_PK_MAX; }
     unsigned m = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);
+    if (G == 32) {
+        // a pixel is the whole warp: one REDUX instead of a five-step shuffle butterfly
+        mm = __reduce_min_sync(FULL, min(m & 0xffffu, m >> 16)) * 0x10001u;
+    } else {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G));
-    mm = __vminu2(m, __byte_perm(m, 0, 0x1032));
+        for (int o = G / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G));
+        mm = __vminu2(m, __byte_perm(m, 0, 0x1032));
+    }
     L[0] = n0; L[1] = n1; L[2] = n2; L[3] = n3;
 }
 
@@ -670,8 +675,12 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
                            min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
         key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
                            min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
+        if (G == 32) {
+            key = __reduce_min_sync(FULL, key);
+        } else {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
+            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
+        }
         const int minS = (int)(key >> 16);
         const int best = (int)(key & 0xffffu);
         bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
