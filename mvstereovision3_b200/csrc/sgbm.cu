@@ -389,6 +389,24 @@ __global__ void __launch_bounds__(VsGeom<G, WIDE>::THREADS) k_sgbm_vsum(VsArgs a
 // Off-domain predecessor == state (L = 0, mm = 0), which yields L = C.
 // PAD: numDisp is not 8*G, lanes with q*8 >= D hold the constant 0x7fff (the out-of-range neighbour value).
 // ------------------------------------------------------------------------------------------------
+// minimum of a 32-bit value over the G lanes of a pixel: REDUX where a pixel is the whole warp or half of it (two
+// warp-wide reductions with the other half masked out), shuffle butterfly below that
+template <int G>
+__device__ __forceinline__ unsigned group_min_u32(unsigned v)
+{
+    if constexpr (G == 32) {
+        return __reduce_min_sync(FULL, v);
+    } else if constexpr (G == 16) {
+        const bool upper = (threadIdx.x & 16) != 0;
+        const unsigned r0 = __reduce_min_sync(FULL, upper ? 0xffffffffu : v), r1 = __reduce_min_sync(FULL, upper ? v : 0xffffffffu);
+        return upper ? r1 : r0;
+    } else {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o, G));
+        return v;
+    }
+}
+
 template <int G, bool PAD>
 __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const uint4& C, unsigned P1P1, unsigned P2P2,
                                          int q, bool padLane)
@@ -417,9 +435,9 @@ __device__ __forceinline__ void sgm_step(unsigned (&L)[4], unsigned& mm, const u
     unsigned n3 = __vimin3_u16x2(X3, X4, __vminu2(L[3], mP2)) + C.w - mm;
     if (PAD && padLane) { n0 = n1 = n2 = n3 = MVSV_PK_MAX; }
     unsigned m = __vminu2(__vimin3_u16x2(n0, n1, n2), n3);
-    if (G == 32) {
-        // a pixel is the whole warp: one REDUX instead of a five-step shuffle butterfly
-        mm = __reduce_min_sync(FULL, min(m & 0xffffu, m >> 16)) * 0x10001u;
+    if (G >= 16) {
+        // a pixel is the whole warp or half of it: REDUX instead of a five- / four-step shuffle butterfly
+        mm = group_min_u32<G>(min(m & 0xffffu, m >> 16)) * 0x10001u;
     } else {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) m = __vminu2(m, __shfl_xor_sync(FULL, m, o, G));
@@ -675,12 +693,7 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
                            min((Sf[1] << 16) | (kb + 2), (Sf[1] & 0xffff0000u) | (kb + 3)));
         key = min(key, min(min((Sf[2] << 16) | (kb + 4), (Sf[2] & 0xffff0000u) | (kb + 5)),
                            min((Sf[3] << 16) | (kb + 6), (Sf[3] & 0xffff0000u) | (kb + 7))));
-        if (G == 32) {
-            key = __reduce_min_sync(FULL, key);
-        } else {
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(FULL, key, o, G));
-        }
+        key = group_min_u32<G>(key);
         const int minS = (int)(key >> 16);
         const int best = (int)(key & 0xffffu);
         bool reject = (minS >= MVSV_MAX_COST);      // every S[d] saturated: best = -1, output stays INVALID
