@@ -703,14 +703,33 @@ __global__ void __launch_bounds__(128) k_sgbm_h2_wta(AggArgs a)
         const unsigned vm = spix[alt + im], vp = spix[alt + ip];
         alt ^= 128 * 8;
         if (a.uniq > 0) {
-            // (a packed count of the sums below floor((minS * 100 - 1) / (100 - uniq)) was measured slower: the division
-            // per step costs more than the eight multiply-compares)
+            // Rejected when some disparity further than 1 from the winner has S * (100 - uniq) < minS * 100.  The test is
+            // monotone in S (100 - uniq > 0), so the lane only needs the smallest of its sums outside best-1..best+1:
+            // the (at most three) exempt positions are overwritten with 0xffff -- no real sum exceeds 0x7fff -- by a
+            // packed compare of the lane's disparity indices against best-1, then one packed min tree and one multiply.
+            // (A packed count of the sums below floor((minS * 100 - 1) / (100 - uniq)) was measured slower: the division
+            // per step costs more than eight multiply-compares.)
             bool bad = false;
+            if (umul > 0) {
+                if (!(PAD && padLane)) {
+                    const unsigned b1 = ((unsigned)(best - 1) & 0xffffu) * 0x10001u;    // best - 1 mod 2^16 in both halves (best may be 0)
+                    unsigned mn = 0xffffffffu;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int kk = (int)kb + j;
-                const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
-                bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
+                    for (int r = 0; r < 4; ++r) {
+                        const unsigned kk2 = (kb + 2u * r) * 0x10001u + 0x00010000u;    // (kb + 2r, kb + 2r + 1)
+                        const unsigned ex = __vcmpleu2(__vsub2(kk2, b1), 0x00020002u);  // 0xffff where |k - best| <= 1
+                        mn = __vminu2(mn, Sf[r] | ex);
+                    }
+                    const int s = (int)min(mn & 0xffffu, mn >> 16);
+                    bad = s <= 0x7fff && s * umul < minS * 100;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kk = (int)kb + j;
+                    const int s = (int)((j & 1) ? (Sf[j >> 1] >> 16) : (Sf[j >> 1] & 0xffffu));
+                    bad |= (!PAD || kk < a.D) && (s * umul < minS * 100) && (abs(kk - best) > 1);
+                }
             }
             reject |= group_any<G>(bad);
         }
